@@ -1,0 +1,135 @@
+/* C ABI of the B200-native Tuatara OCR hot path (libtuatara_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch/OpenCV types, no
+ * exceptions.  Every function returns 0 on success and non-zero on failure; the message is
+ * available from tt_last_error() (thread-local).  The reference has no FFI of its own -- its
+ * boundary is the C++ function image_to_data (tuatara.h:13) and the pybind11 module
+ * (bindings/python.cpp:54-58); include/tuatara.h and tuatara_b200/bindings/python.cpp re-create
+ * those on top of this ABI.  Each entry point cites the reference code it replaces.
+ */
+#ifndef TUATARA_C_H
+#define TUATARA_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define TT_API __attribute__((visibility("default")))
+#else
+#define TT_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TT_MAX_LABEL_LEN 26  /* PARSeq positions per crop (max_label_length + 1) */
+#define TT_NUM_CLASSES 95    /* logits per position */
+
+typedef struct tt_engine tt_engine;
+
+/* A caller-owned 8-bit, 3-channel, row-major image (the cv::Mat of tuatara.h:13 without OpenCV).
+ * The buffer is only read (the reference swaps channels in place at tuatara.cpp:349; here the
+ * swap happens inside the kernels). */
+typedef struct tt_image {
+  const uint8_t* data;
+  int rows, cols, channels; /* channels must be 3 */
+  size_t step;              /* bytes per row */
+} tt_image;
+
+/* Every literal of the reference gathered in one struct (the TODO at tuatara.cpp:396). */
+typedef struct tt_config {
+  float canvas_size;    /* 1024  tuatara.cpp:352 */
+  float mag_ratio;      /* 1.0   tuatara.cpp:353 */
+  float text_threshold; /* 0.7   tuatara.cpp:397 */
+  float link_threshold; /* 0.4   tuatara.cpp:398 */
+  float low_text;       /* 0.4   tuatara.cpp:399 */
+  int min_area;         /* 10    tuatara.cpp:148 */
+  int max_batch_pages;  /* pages processed per CRAFT batch per GPU (0 = default) */
+  int reserved;
+} tt_config;
+
+typedef struct tt_item {
+  char* text;    /* NUL-terminated, owned by the result */
+  float bbox[4]; /* min_x, min_y, max_x, max_y (tuatara.cpp:256-274) */
+} tt_item;
+typedef struct tt_page_result {
+  int n_items;
+  tt_item* items; /* in CCL label order (tuatara.cpp:146) */
+} tt_page_result;
+typedef struct tt_result {
+  int n_pages;
+  tt_page_result* pages;
+} tt_result;
+
+/* ---------------------------------------------------------------- whole path */
+TT_API void tt_config_default(tt_config* cfg);
+TT_API const char* tt_last_error(void);
+/* Engine = weights resident on each listed device + streams + workspaces.  Replaces the two
+ * torch::jit::load calls per image (tuatara.cpp:333-336, :423-428): weights_dir must hold
+ * craft.ttw and parseq.ttw (tuatara_b200.weights exporter).  devices == NULL -> {0}. */
+TT_API int tt_engine_create(const char* weights_dir, const int* devices, int n_devices, const tt_config* cfg,
+                     tt_engine** out);
+TT_API void tt_engine_destroy(tt_engine* e);
+/* image_to_data (tuatara.cpp:314-512) for a batch of pages; pages are sharded over the engine's
+ * GPUs, results gathered on the host in page order. */
+TT_API int tt_ocr_pages(tt_engine* e, const tt_image* pages, int n_pages, tt_result** out);
+TT_API void tt_result_free(tt_result* r);
+/* Kernel launches issued by this library so far (bench.py's gpu_launches). */
+TT_API unsigned long long tt_launch_count(void);
+
+/* ---------------------------------------------------- stage level, host memory */
+/* Size arithmetic of resize_aspect_ratio (tuatara.cpp:211-226), fp32 like the reference. */
+TT_API int tt_resize_plan(int rows, int cols, float canvas_size, float mag_ratio, int* target_h, int* target_w, int* h32,
+                   int* w32, float* ratio);
+/* Channel swap + resize + zero pad (tuatara.cpp:349, :206-234). out: h32*w32*3 bytes. */
+TT_API int tt_preprocess(const tt_image* image, float canvas_size, float mag_ratio, uint8_t* out);
+/* CRAFT forward (tuatara.cpp:363-394). craft_input = tt_preprocess output; maps_out: [h32/2][w32/2][2] fp32. */
+TT_API int tt_craft_forward(tt_engine* e, const uint8_t* craft_input, int h32, int w32, float* maps_out);
+/* get_detected_boxes (tuatara.cpp:119-204) on one score map [H][W][2].
+ *  labels_out  (nullable) [H*W] int32          == cv::connectedComponentsWithStats labels
+ *  stats_out   (nullable) [stats_cap][5] int32 == its stats rows (left, top, width, height, area), row 0 = background
+ *  rects_out   [rect_cap][5] fp32 (cx, cy, w, h, angle) of the kept components, rect_labels_out their labels */
+TT_API int tt_postprocess(const float* maps, int H, int W, const tt_config* cfg, int32_t* labels_out, int32_t* stats_out,
+                   int stats_cap, int* n_labels, float* rects_out, int32_t* rect_labels_out, int rect_cap,
+                   int* n_rects);
+/* Crop + resize to 128x32 (tuatara.cpp:416, :440-441). rects_xywh already clamped to the image.
+ * out: [n][32][128][3] u8 in the caller's channel order. */
+TT_API int tt_crop_resize(const tt_image* image, const int32_t* rects_xywh, int n, uint8_t* out);
+/* PARSeq forward (tuatara.cpp:307, 26 AR steps + 1 refinement). crops: [n][32][128][3] u8.
+ * forced_tokens (nullable) [n][25]: teacher-forced AR context (parity tests).
+ * logits_out (nullable) [n][26][95] fp32; ids_out (nullable) [n][26] argmax (== softmax + max, :486,:103). */
+TT_API int tt_parseq_forward(tt_engine* e, const uint8_t* crops, int n, const int32_t* forced_tokens, float* logits_out,
+                      int32_t* ids_out);
+/* Tokenizer::decode + truncation (tuatara.cpp:61-116, :497-502). ids [n][len]; out [n][out_stride] chars. */
+TT_API int tt_decode(const int32_t* ids, int n, int len, char* out, int out_stride);
+/* itos_out: >= 99 bytes. */
+TT_API int tt_tokenizer_table(char* itos_out, int* eos_id, int* bos_id, int* pad_id);
+
+/* ------------------------------------------------- host geometry (no GPU needed) */
+TT_API int tt_convex_hull_i32(const int32_t* xy, int n, int32_t* idx_out, int* n_out);
+TT_API int tt_convex_hull_f32(const float* xy, int n, int32_t* idx_out, int* n_out);
+TT_API int tt_min_area_rect_i32(const int32_t* xy, int n, float rect_out[5]);
+TT_API int tt_min_area_rect_f32(const float* xy, int n, float rect_out[5]);
+TT_API int tt_rect_points(const float rect[5], float pts_out[8]);
+TT_API int tt_rect_bounding(const float rect[5], int32_t xywh_out[4]);
+TT_API int tt_adjust_rect(const float rect[5], float ratio_w, float ratio_h, float ratio_net, float rect_out[5]);
+TT_API int tt_rect_to_bbox(const float rect[5], float bbox_out[4]);
+
+/* --------------------------------------- stage level, device memory (bench / kernel tests) */
+/* out[M][N] = act(A[M][K] * W[N][K]^T + bias) (+ residual). All pointers are device pointers;
+ * A, W bf16; bias fp32; out bf16 (out_f32 == 0) or fp32. act: 0 none, 1 relu, 2 gelu. */
+TT_API int tt_linear_dev(const void* A, int lda, int M, int K, const void* W, int N, const float* bias, int act,
+                  const void* residual, int res_f32, int ldr, void* out, int out_f32, int ldc, int BN, void* stream);
+/* NHWC bf16 stride-1 "same" convolution as implicit GEMM; src1 may be NULL (else channel concat).
+ * weight bf16 [Cout][taps][C0+C1]; out bf16 [batch][H][W][Cout]. */
+TT_API int tt_conv_dev(const void* src0, int C0, const void* src1, int C1, int batch, int H, int W, int taps, int dil,
+                const void* weight, const float* bias, int Cout, int relu, void* out, int BN, void* stream);
+/* Batched device-side post-processing (bench): maps_dev [batch][H][W][2] fp32. Returns total rects. */
+TT_API int tt_postprocess_dev(tt_engine* e, const float* maps_dev, int batch, int H, int W, int* n_rects_total,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TUATARA_C_H */

@@ -1,0 +1,33 @@
+// Shared host-side helpers: thread-local error string (behind tt_last_error), CUDA status
+// macros, a global kernel-launch counter (bench.py reports it as gpu_launches).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <string>
+
+namespace tt {
+
+void set_error(const std::string& msg);
+const char* last_error();
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace tt
+
+#define TT_CUDA_TRY(expr)                                                                     \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      tt::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                    std::to_string(__LINE__) + ")");                                          \
+      return _e;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+#define TT_LAUNCH_CHECK()                                          \
+  do {                                                             \
+    tt::count_launch();                                            \
+    TT_CUDA_TRY(cudaGetLastError());                               \
+  } while (0)

@@ -1,0 +1,66 @@
+// Host-side interface of the one tensor-core kernel both networks run on:
+//   out[M x N] = epilogue( A[M x K] * Wt[N x K]^T )      bf16 x bf16 -> fp32 (TMEM) -> bf16/fp32
+// A is either a plain row-major matrix (PARSeq linears) or an NHWC activation read as an
+// implicit GEMM (CRAFT convs: per-tap shifted TMA boxes, OOB zero fill == zero padding,
+// optional second source == channel concat without materialising it).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tt {
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+enum ResType : int { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2 };
+enum OutType : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_CLS_TAIL = 2 };
+
+struct Epilogue {
+  const float* bias = nullptr;      // [N] fp32 (BatchNorm already folded in)
+  int act = ACT_NONE;
+  const void* residual = nullptr;   // added after bias, before activation==NONE only
+  int res_type = RES_NONE;
+  int ldr = 0;                      // residual row pitch (elements)
+  int res_mod = 0;                  // >0: residual row = m % res_mod (positional table)
+  void* out = nullptr;
+  int out_type = OUT_BF16;
+  int ldc = 0;                      // output row pitch (elements)
+  void* out2 = nullptr;             // optional second copy of the bf16 output (same pitch)
+  // OUT_CLS_TAIL: after bias+ReLU on the 16 accumulators, two 1x1 convs in registers
+  // (16->16 ReLU, 16->2) and an fp32 [pixel][2] store.  tail = {w4[16][16], b4[16], w5[2][16], b5[2]}
+  const float* tail = nullptr;
+};
+
+struct ConvSrc {
+  const __nv_bfloat16* ptr = nullptr;  // NHWC
+  int C = 0;                           // channels used from this source
+  int pitch = 0;                       // channel pitch of the buffer (>= C)
+};
+
+struct ConvProblem {
+  int batch = 1, H = 0, W = 0;    // stride-1 "same" conv: input and output share H x W
+  ConvSrc src[2];
+  int nsrc = 1;
+  int taps = 9;                   // 9 (3x3) or 1 (1x1)
+  int dil = 1;
+  const __nv_bfloat16* weight = nullptr;  // [Cout][taps][C0 + C1], K-major
+  int Cout = 0;
+  int BN = 0;                     // 0 = choose
+};
+
+struct LinearProblem {
+  const __nv_bfloat16* A = nullptr;  // [M][lda]
+  int lda = 0;
+  int M = 0, K = 0;
+  const __nv_bfloat16* W = nullptr;  // [N][K]
+  int N = 0;
+  int BN = 0;
+};
+
+// Both return cudaSuccess or the first error (also recorded via tt::set_error).
+cudaError_t conv_forward(const ConvProblem& p, const Epilogue& e, cudaStream_t s);
+cudaError_t linear_forward(const LinearProblem& p, const Epilogue& e, cudaStream_t s);
+
+// Number of kernel launches issued through the two entry points above (bench bookkeeping).
+uint64_t gemm_launch_count();
+
+}  // namespace tt
