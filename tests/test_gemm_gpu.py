@@ -1,0 +1,100 @@
+"""tcgen05 GEMM / implicit-GEMM conv kernel vs a plain fp32 torch reference of the same op
+(floating-point kernel: bf16 operands, fp32 accumulation).  Tolerance: the inputs are
+bf16-exact, so the only error sources are accumulation order and the bf16 rounding of the
+output: |err| <= 2^-8 * |ref| + 1e-3 * sqrt(K)-scaled slack."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lin(native_lib, M, K, N, act=0, bias=True, res=None, out_f32=False, BN=0, seed=0):
+    from tuatara_b200._native import check
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    b = (torch.randn(N, generator=g)).float().cuda() if bias else None
+    R = None
+    if res == "bf16":
+        R = torch.randn(M, N, generator=g).to(torch.bfloat16).cuda()
+    elif res == "f32":
+        R = torch.randn(M, N, generator=g).float().cuda()
+    out = torch.full((M, N), float("nan"), dtype=torch.float32 if out_f32 else torch.bfloat16, device="cuda")
+    check(native_lib.tt_linear_dev(A.data_ptr(), K, M, K, W.data_ptr(), N, b.data_ptr() if bias else None, act,
+                                   R.data_ptr() if R is not None else None, int(res == "f32"), N,
+                                   out.data_ptr(), int(out_f32), N, BN, None), "tt_linear_dev")
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t()
+    if bias:
+        ref = ref + b
+    if R is not None:
+        ref = ref + R.float()
+    if act == 1:
+        ref = torch.relu(ref)
+    elif act == 2:
+        ref = torch.nn.functional.gelu(ref)
+    return out.float().cpu(), ref.cpu()
+
+
+def _check(out, ref, K, what):
+    assert torch.isfinite(out).all(), f"{what}: non-finite output (unwritten tiles?)"
+    err = (out - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-3 * np.sqrt(K)
+    bad = err > tol
+    if bad.any():
+        idx = bad.nonzero()
+        rows = idx[:, 0].unique()[:8].tolist()
+        cols = idx[:, 1].unique()[:16].tolist()
+        raise AssertionError(f"{what}: {int(bad.sum())}/{bad.numel()} elements off, max err {float(err.max()):.4g}; "
+                             f"first bad rows {rows} cols {cols}; out[0,:8]={out[0,:8].tolist()} ref[0,:8]={ref[0,:8].tolist()}")
+
+
+@pytest.mark.parametrize("M,K,N,BN", [
+    (128, 64, 64, 64), (128, 128, 128, 128), (256, 64, 256, 256), (1000, 384, 1152, 0), (4096, 1536, 384, 0),
+    (333, 96, 384, 0), (77, 384, 96, 96), (512, 384, 1536, 256), (128, 64, 16, 16), (300, 32, 32, 32),
+    (20000, 384, 384, 192),
+])
+def test_linear_shapes(native_lib, M, K, N, BN):
+    out, ref = _lin(native_lib, M, K, N, BN=BN)
+    _check(out, ref, K, f"linear M{M} K{K} N{N} BN{BN}")
+
+
+@pytest.mark.parametrize("act,res,out_f32", [(1, None, False), (2, None, False), (0, "bf16", False),
+                                             (0, "f32", True), (0, None, True)])
+def test_linear_epilogues(native_lib, act, res, out_f32):
+    out, ref = _lin(native_lib, 700, 384, 384, act=act, res=res, out_f32=out_f32)
+    _check(out, ref, 384, f"linear act{act} res{res} f32{out_f32}")
+
+
+def _conv(native_lib, B, H, W, C0, C1, Cout, taps, dil, relu=1, BN=0, seed=0):
+    from tuatara_b200._native import check
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x0 = (torch.randn(B, H, W, C0, generator=g)).to(torch.bfloat16).cuda()
+    x1 = (torch.randn(B, H, W, C1, generator=g)).to(torch.bfloat16).cuda() if C1 else None
+    ct = C0 + C1
+    k = 3 if taps == 9 else 1
+    w = (torch.randn(Cout, k, k, ct, generator=g) * (1.0 / np.sqrt(taps * ct))).to(torch.bfloat16).cuda()
+    b = torch.randn(Cout, generator=g).float().cuda()
+    out = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    check(native_lib.tt_conv_dev(x0.data_ptr(), C0, x1.data_ptr() if C1 else None, C1, B, H, W, taps, dil,
+                                 w.data_ptr(), b.data_ptr(), Cout, relu, out.data_ptr(), BN, None), "tt_conv_dev")
+    torch.cuda.synchronize()
+    xin = x0.float() if not C1 else torch.cat([x0.float(), x1.float()], -1)
+    ref = torch.nn.functional.conv2d(xin.permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b,
+                                     padding=(dil if taps == 9 else 0), dilation=dil)
+    if relu:
+        ref = torch.relu(ref)
+    return out.float().cpu(), ref.permute(0, 2, 3, 1).contiguous().cpu()
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,taps,dil", [
+    (1, 32, 48, 64, 0, 64, 9, 1), (2, 24, 38, 128, 0, 256, 9, 1), (1, 16, 16, 512, 0, 1024, 9, 6),
+    (1, 48, 38, 1024, 512, 512, 1, 1), (1, 64, 64, 32, 0, 32, 9, 1), (1, 40, 24, 32, 0, 16, 9, 1),
+    (1, 64, 80, 32, 0, 64, 1, 1), (1, 14, 18, 64, 0, 128, 9, 1), (3, 8, 8, 256, 128, 128, 1, 1),
+])
+def test_conv_shapes(native_lib, B, H, W, C0, C1, Cout, taps, dil):
+    out, ref = _conv(native_lib, B, H, W, C0, C1, Cout, taps, dil)
+    _check(out.reshape(-1, Cout), ref.reshape(-1, Cout), taps * (C0 + C1), f"conv {B}x{H}x{W} C{C0}+{C1}->{Cout} t{taps} d{dil}")

@@ -1,0 +1,112 @@
+"""Integer / byte stages on the GPU vs the oracle (cv2): bit-exact."""
+import cv2
+import numpy as np
+import pytest
+import torch
+
+import tuatara_b200 as tb
+from oracle import tuatara_ref as R
+from tuatara_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rect_bits(r):
+    return np.array([r[0][0], r[0][1], r[1][0], r[1][1], r[2]], np.float32).view(np.uint32)
+
+
+def _post_case(maps):
+    det, dbg = R.get_detected_boxes(torch.from_numpy(maps[..., 0].copy()), torch.from_numpy(maps[..., 1].copy()),
+                                    0.7, 0.4, 0.4)
+    got = tb.postprocess(maps)
+    assert got["n_labels"] == dbg.n_labels
+    assert np.array_equal(got["labels"], dbg.labels), "CCL labels differ from cv::connectedComponentsWithStats"
+    assert np.array_equal(got["stats"][1:], dbg.stats[1:, :5]), "component stats differ"
+    assert got["stats"][0, 4] == dbg.stats[0, 4]
+    assert list(got["rect_labels"]) == dbg.mapper, "kept components differ"
+    assert len(got["rects"]) == len(det)
+    for i, (a, b) in enumerate(zip(got["rects"], det)):
+        assert np.array_equal(_rect_bits(a), _rect_bits(b)), f"rect {i}: {a} vs {b}"
+    return len(det)
+
+
+@pytest.mark.parametrize("page", [0, 1, 7])
+def test_postprocess_synth_page(native_lib, page):
+    assert _post_case(synth.synth_score_maps(page)) == 300
+
+
+@pytest.mark.parametrize("seed,h,w", [(0, 384, 304), (1, 512, 384), (2, 512, 512), (3, 97, 131), (4, 33, 1000),
+                                      (5, 256, 256), (6, 64, 40)])
+def test_postprocess_random_blobs(native_lib, seed, h, w):
+    _post_case(synth.random_blob_maps(seed, h, w))
+
+
+@pytest.mark.parametrize("seed,p", [(0, 0.5), (1, 0.3), (2, 0.7), (3, 0.05), (4, 0.95)])
+def test_ccl_bernoulli(native_lib, seed, p):
+    """Dense random masks: worst case for the union-find (tens of thousands of components)."""
+    rng = np.random.default_rng(seed)
+    h, w = 200 + 13 * seed, 300 - 17 * seed
+    m = np.zeros((h, w, 2), np.float32)
+    m[..., 0] = (rng.random((h, w)) < p).astype(np.float32)
+    m[0, 0, 0], m[0, 1, 0] = 0.0, 1.0  # pin min/max so normalisation is the identity
+    m[..., 1] = 0.0
+    m[0, 0, 1], m[0, 1, 1] = 0.0, 1.0
+    m[0, 1, 1] = 1.0
+    _post_case(m)
+
+
+def test_postprocess_degenerate(native_lib):
+    flat = np.full((64, 64, 2), 0.25, np.float32)  # max == min -> NaN maps -> no components (reference: 0 boxes)
+    got = tb.postprocess(flat)
+    assert got["n_labels"] == 1 and len(got["rects"]) == 0
+    one = np.zeros((40, 50, 2), np.float32)
+    one[10:30, 5:45, 0] = 1.0
+    _post_case(one)
+    edge = np.zeros((40, 50, 2), np.float32)  # components touching every border
+    edge[0:3, :, 0] = 1.0
+    edge[-4:, :, 0] = 1.0
+    edge[10:30, 0:5, 0] = 0.9
+    edge[10:30, -6:, 0] = 0.8
+    edge[18:22, 5:20, 1] = 1.0
+    _post_case(edge)
+
+
+@pytest.mark.parametrize("h,w", [(1280, 1280), (763, 607), (1000, 754), (664, 1245), (206, 275), (2000, 1128),
+                                 (1171, 3000), (1024, 1024), (2048, 2048), (31, 57)])
+def test_preprocess_bit_exact(native_lib, h, w):
+    rng = np.random.default_rng(h * 7 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref, ratio, _ = R.resize_aspect_ratio(cv2.cvtColor(img, cv2.COLOR_BGR2RGB), 1024, cv2.INTER_LINEAR, 1.0)
+    got, got_ratio = tb.preprocess(img)
+    assert got.shape == ref.shape
+    assert np.float32(ratio) == np.float32(got_ratio)
+    assert np.array_equal(got, ref), f"{int((got != ref).sum())} bytes differ"
+
+
+def test_crop_resize_bit_exact(native_lib):
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (700, 900, 3), dtype=np.uint8)
+    rects = []
+    for _ in range(200):
+        w, h = int(rng.integers(1, 400)), int(rng.integers(1, 200))
+        x, y = int(rng.integers(0, 900 - w + 1)), int(rng.integers(0, 700 - h + 1))
+        rects.append((x, y, w, h))
+    rects += [(0, 0, 900, 700), (10, 10, 256, 64), (5, 5, 128, 32), (0, 0, 1, 1), (3, 4, 2, 1), (7, 9, 512, 96)]
+    swapped = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+    ref = np.stack([R.crop_to_parseq_u8(swapped, r) for r in rects])
+    got = tb.crop_resize(img, rects)
+    assert np.array_equal(got, ref), f"{int((got != ref).sum())} bytes differ"
+
+
+def test_crop_resize_synth_page(native_lib):
+    img = synth.synth_page(2)
+    maps = synth.synth_score_maps(2)
+    det, _ = R.get_detected_boxes(torch.from_numpy(maps[..., 0].copy()), torch.from_numpy(maps[..., 1].copy()),
+                                  0.7, 0.4, 0.4)
+    inv = np.float32(1) / np.float32(0.8)
+    boxes = R.adjust_result_coordinates(det, inv, inv)
+    rects = [R.crop_rect(img.shape, b)[:4] for b in boxes]
+    swapped = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+    ref = np.stack([R.crop_to_parseq_u8(swapped, r) for r in rects])
+    got = tb.crop_resize(img, rects)
+    assert np.array_equal(got, ref)

@@ -38,10 +38,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (-> launch error the host reports) instead of hanging
-// the GPU.  The bound (~2^28 polls, each a HW-suspended try_wait) is seconds, far above any
+// the GPU.  The bound (2^22 polls, each a HW-suspended try_wait) is seconds, far above any
 // legitimate wait in these kernels.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 28); ++i)
+#pragma unroll 1
+  for (uint32_t i = 0; i < (1u << 22); ++i)
     if (mbar_try_wait(bar, parity)) return;
   __trap();
 }
