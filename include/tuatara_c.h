@@ -74,6 +74,18 @@ TT_API void tt_engine_destroy(tt_engine* e);
 /* image_to_data (tuatara.cpp:314-512) for a batch of pages; pages are sharded over the engine's
  * GPUs, results gathered on the host in page order. */
 TT_API int tt_ocr_pages(tt_engine* e, const tt_image* pages, int n_pages, tt_result** out);
+/* Same, with options the benchmark and the parity tests need.
+ *  pages_on_device: tt_image.data are device pointers (page i on the GPU that gets page i, i.e.
+ *    engine device i % n_devices) -- throughput with inputs already resident in HBM.
+ *  score_override: NULL, or n_pages pointers (NULL entries allowed) to fp32 [h32/2][w32/2][2] maps
+ *    that replace CRAFT's output for that page AFTER CRAFT has run in full (random-init weights
+ *    give near-constant maps).  override_on_device: those pointers are device memory. */
+typedef struct tt_ocr_options {
+  int pages_on_device;
+  int override_on_device;
+  const float* const* score_override;
+} tt_ocr_options;
+TT_API int tt_ocr_pages_ex(tt_engine* e, const tt_image* pages, int n_pages, const tt_ocr_options* opt, tt_result** out);
 TT_API void tt_result_free(tt_result* r);
 /* Kernel launches issued by this library so far (bench.py's gpu_launches). */
 TT_API unsigned long long tt_launch_count(void);

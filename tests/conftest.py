@@ -39,3 +39,35 @@ def native_lib():
     if not _native.LIB_PATH.exists():
         build.build()
     return _native.lib()
+
+
+@pytest.fixture(scope="session")
+def oracle_models():
+    """Seeded random-init fp32 oracle networks (checkpoints are unavailable offline)."""
+    from oracle.models import make_craft, make_parseq
+
+    return make_craft(0), make_parseq("base", 0)
+
+
+@pytest.fixture(scope="session")
+def weights_dir(oracle_models):
+    """craft.ttw / parseq.ttw exported from the oracle models (cached under tests/_cache)."""
+    from tuatara_b200 import weights
+
+    d = ROOT / "tests" / "_cache" / "weights_seed0"
+    d.mkdir(parents=True, exist_ok=True)
+    craft, parseq = oracle_models
+    if not (d / "craft.ttw").exists():
+        weights.export_craft(craft.state_dict(), d / "craft.ttw")
+    if not (d / "parseq.ttw").exists():
+        weights.export_parseq(parseq.state_dict(), d / "parseq.ttw")
+    return str(d)
+
+
+@pytest.fixture(scope="session")
+def engine(native_lib, weights_dir):
+    import tuatara_b200 as tb
+
+    e = tb.Engine(weights_dir)
+    yield e
+    e.close()

@@ -174,12 +174,34 @@ class Engine:
 
     __del__ = close
 
-    def ocr_pages(self, images: list[np.ndarray]) -> list[list[dict]]:
+    def ocr_pages(self, images: list, score_override: list | None = None) -> list[list[dict]]:
+        """images: uint8 [H,W,3] numpy arrays (host) or torch CUDA tensors (already on the device).
+        score_override: optional per-page float32 [h32/2, w32/2, 2] maps (numpy or CUDA tensors, or
+        None entries) that replace CRAFT's output after CRAFT has run (benchmark / parity tests)."""
         n = len(images)
-        structs = [_native.image_struct(im) for im in images]
+        on_dev = n > 0 and not isinstance(images[0], np.ndarray)
+        if on_dev:
+            structs = [_native.tt_image(t.data_ptr(), t.shape[0], t.shape[1], t.shape[2], t.stride(0)) for t in images]
+        else:
+            structs = [_native.image_struct(im) for im in images]
         arr = (_native.tt_image * n)(*structs)
+        opt = _native.tt_ocr_options(int(on_dev), 0, None)
+        keep = []
+        if score_override is not None:
+            ov_dev = any(m is not None and not isinstance(m, np.ndarray) for m in score_override)
+            ptrs = (C.c_void_p * n)()
+            for i, m in enumerate(score_override):
+                if m is None:
+                    ptrs[i] = None
+                    continue
+                if isinstance(m, np.ndarray):
+                    m = np.ascontiguousarray(m, np.float32)
+                keep.append(m)
+                ptrs[i] = ptr(m)
+            opt.override_on_device = int(ov_dev)
+            opt.score_override = ptrs
         res = C.POINTER(_native.tt_result)()
-        check(lib().tt_ocr_pages(self._h, arr, n, C.byref(res)), "tt_ocr_pages")
+        check(lib().tt_ocr_pages_ex(self._h, arr, n, C.byref(opt), C.byref(res)), "tt_ocr_pages_ex")
         try:
             out = []
             for p in range(res.contents.n_pages):

@@ -28,6 +28,11 @@ class tt_config(C.Structure):
                 ("max_batch_pages", C.c_int), ("reserved", C.c_int)]
 
 
+class tt_ocr_options(C.Structure):
+    _fields_ = [("pages_on_device", C.c_int), ("override_on_device", C.c_int),
+                ("score_override", C.POINTER(C.c_void_p))]
+
+
 class tt_item(C.Structure):
     _fields_ = [("text", C.c_char_p), ("bbox", C.c_float * 4)]
 
@@ -53,6 +58,7 @@ SIGNATURES = {
     "tt_engine_create": (_I, [C.c_char_p, _PI, _I, C.POINTER(tt_config), C.POINTER(_P)]),
     "tt_engine_destroy": (None, [_P]),
     "tt_ocr_pages": (_I, [_P, C.POINTER(tt_image), _I, C.POINTER(C.POINTER(tt_result))]),
+    "tt_ocr_pages_ex": (_I, [_P, C.POINTER(tt_image), _I, C.POINTER(tt_ocr_options), C.POINTER(C.POINTER(tt_result))]),
     "tt_result_free": (None, [C.POINTER(tt_result)]),
     "tt_launch_count": (C.c_ulonglong, []),
     "tt_resize_plan": (_I, [_I, _I, _F, _F, _PI, _PI, _PI, _PI, _PF]),

@@ -13,6 +13,8 @@ void set_error(const std::string& msg);
 const char* last_error();
 extern std::atomic<unsigned long long> g_launches;
 inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device: set it once per (kernel, device).
+cudaError_t ensure_dynamic_smem(const void* func, int bytes);
 
 }  // namespace tt
 

@@ -1,6 +1,91 @@
 // The engine behind tt_engine_*: per-GPU weight replicas, streams and workspaces; pages are
 // sharded over GPUs by one host worker thread per device, results gathered on the host.
+// Replaces the orchestration of image_to_data (tuatara.cpp:314-512).
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "detect.h"
+#include "postprocess.cuh"
 #include "tuatara_c.h"
 
-struct tt_engine;  // defined in engine.cpp
+namespace tt {
+
+struct WTensor {
+  void* ptr = nullptr;
+  int dtype = 0;  // 0 f32, 1 bf16, 2 i32
+  std::vector<long long> dims;
+  size_t nbytes = 0;
+};
+
+// A .ttw file resident on one device (tuatara_b200/weights.py documents the format).
+class WeightFile {
+ public:
+  ~WeightFile();
+  bool load(const std::string& path, std::vector<int>* meta_out = nullptr);
+  const WTensor& get(const std::string& name) const;  // throws std::runtime_error when missing
+  const __nv_bfloat16* bf(const std::string& name) const { return static_cast<const __nv_bfloat16*>(get(name).ptr); }
+  const float* f32(const std::string& name) const { return static_cast<const float*>(get(name).ptr); }
+
+ private:
+  std::map<std::string, WTensor> t_;
+  void* arena_ = nullptr;
+};
+
+// Grow-only device scratch: reset() at the start of a forward pass, alloc() bumps.
+class Arena {
+ public:
+  ~Arena();
+  cudaError_t reserve(size_t bytes);
+  void reset() { off_ = 0; }
+  void* alloc(size_t bytes);  // nullptr when exhausted (caller reserved too little)
+  template <class T> T* get(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
+  size_t capacity() const { return cap_; }
+
+ private:
+  uint8_t* base_ = nullptr;
+  size_t cap_ = 0, off_ = 0;
+};
+
+struct ParseqDims {
+  int D = 384, depth = 12, enc_heads = 6, dec_heads = 12, mlp = 1536, n_cls = 95, L = 26, n_tok = 97;
+  int n_cls_pad = 96;
+  int eos_id = 0, bos_id = 95, pad_id = 96;
+};
+
+struct DeviceCtx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  WeightFile craft, parseq;
+  ParseqDims pd;
+  Arena arena;
+  float* q_sa_table = nullptr;  // [L][D] fp32: self-attn queries of the 26 positions (crop independent)
+  PostWorkspace post;           // sized lazily for (batch, H, W)
+  uint8_t* pinned = nullptr;    // host staging for D2H of post results / ids
+  size_t pinned_bytes = 0;
+  std::mutex mu;                // one request at a time per device
+
+  ~DeviceCtx();
+  cudaError_t init(const std::string& weights_dir);
+  cudaError_t ensure_pinned(size_t bytes);
+  // CRAFT: device u8 [B][H][W][3] (already swapped/padded) -> device fp32 maps [B][H/2][W/2][2] (arena memory)
+  cudaError_t craft_forward(const uint8_t* input_dev, int B, int H, int W, float** maps_out);
+  size_t craft_bytes(int B, int H, int W) const;
+  // PARSeq: device bf16 patches [n*128][96] -> device fp32 logits [n][L][n_cls_pad] + int ids [n][L] (arena)
+  cudaError_t parseq_forward(const __nv_bfloat16* patches_dev, int n, const int* forced_dev, float** logits_out,
+                             int** ids_out);
+  size_t parseq_bytes(int n) const;
+};
+
+}  // namespace tt
+
+struct tt_engine {
+  tt_config cfg;
+  std::vector<std::unique_ptr<tt::DeviceCtx>> devs;
+};

@@ -341,8 +341,10 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-              const cuuint32_t* box, int row_bytes) {
+}  // namespace
+
+bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box, int row_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -360,8 +362,15 @@ bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims
   return true;
 }
 
+namespace {
+
+inline bool make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box, int row_bytes) {
+  return make_tmap_bf16(m, base, rank, dims, strides_bytes, box, row_bytes);
+}
+
 int num_sms() {
-  static int n = 0;
+  static int n = 0;  // all GPUs of one box are the same part
   if (n == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -390,12 +399,7 @@ cudaError_t launch(KParams& kp, cudaStream_t s) {
   const int stage_bytes = kBlockM * row_bytes + kp.BN * row_bytes;
   kp.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - 1024) / stage_bytes));
   const size_t smem = static_cast<size_t>(kp.stages) * stage_bytes + sizeof(SmemCtl) + 1024;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  TT_CUDA_TRY(attr_err);
+  TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_tc_kernel), 227 * 1024));
   const int total = kp.num_m_tiles * kp.num_n_tiles;
   const int grid = std::min(total, num_sms());
   gemm_tc_kernel<<<grid, kThreads, smem, s>>>(kp);

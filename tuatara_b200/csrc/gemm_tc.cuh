@@ -4,6 +4,7 @@
 // implicit GEMM (CRAFT convs: per-tap shifted TMA boxes, OOB zero fill == zero padding,
 // optional second source == channel concat without materialising it).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -59,6 +60,11 @@ struct LinearProblem {
 // Both return cudaSuccess or the first error (also recorded via tt::set_error).
 cudaError_t conv_forward(const ConvProblem& p, const Epilogue& e, cudaStream_t s);
 cudaError_t linear_forward(const LinearProblem& p, const Epilogue& e, cudaStream_t s);
+
+// cuTensorMapEncodeTiled for a bf16 tensor (dims/strides innermost first; strides for dims 1..rank-1 in
+// bytes); row_bytes = box[0]*2 selects the swizzle (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B).
+bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box, int row_bytes);
 
 // Number of kernel launches issued through the two entry points above (bench bookkeeping).
 uint64_t gemm_launch_count();

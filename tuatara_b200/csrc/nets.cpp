@@ -1,0 +1,368 @@
+// CRAFT and PARSeq forward passes assembled from the tcgen05 GEMM kernel (gemm_tc.cu) and the
+// auxiliary kernels (nn_kernels.cu).  These replace `detector_model.forward` (tuatara.cpp:376) and
+// `model.forward` inside infer() (tuatara.cpp:307); the graphs are the upstream architectures the
+// reference's TorchScript files encode (oracle/models.py is the fp32 oracle).
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+
+#include "common.h"
+#include "engine.h"
+#include "gemm_tc.cuh"
+#include "nn_kernels.cuh"
+#include "resize.cuh"
+
+namespace tt {
+
+// ------------------------------------------------------------------------------ WeightFile
+WeightFile::~WeightFile() {
+  if (arena_) cudaFree(arena_);
+}
+
+bool WeightFile::load(const std::string& path, std::vector<int>* meta_out) {
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) { set_error("cannot open weight file " + path); return false; }
+  const size_t size = static_cast<size_t>(f.tellg());
+  f.seekg(0);
+  std::vector<char> buf(size);
+  f.read(buf.data(), static_cast<std::streamsize>(size));
+  if (size < 8 || std::memcmp(buf.data(), "TTW1", 4) != 0) { set_error("bad weight file " + path); return false; }
+  uint32_t n;
+  std::memcpy(&n, buf.data() + 4, 4);
+  if (cudaMalloc(&arena_, size) != cudaSuccess) { set_error("cudaMalloc failed for " + path); return false; }
+  if (cudaMemcpy(arena_, buf.data(), size, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("weight upload failed for " + path);
+    return false;
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    const char* e = buf.data() + 8 + static_cast<size_t>(i) * 120;
+    char name[65] = {0};
+    std::memcpy(name, e, 64);
+    uint32_t dt, nd;
+    uint64_t dims[4], off, nb;
+    std::memcpy(&dt, e + 64, 4);
+    std::memcpy(&nd, e + 68, 4);
+    std::memcpy(dims, e + 72, 32);
+    std::memcpy(&off, e + 104, 8);
+    std::memcpy(&nb, e + 112, 8);
+    if (off + nb > size) { set_error("truncated weight file " + path); return false; }
+    WTensor t;
+    t.ptr = static_cast<char*>(arena_) + off;
+    t.dtype = static_cast<int>(dt);
+    t.nbytes = nb;
+    for (uint32_t k = 0; k < nd; ++k) t.dims.push_back(static_cast<long long>(dims[k]));
+    if (meta_out && std::strcmp(name, "meta") == 0) {
+      meta_out->resize(nb / 4);
+      std::memcpy(meta_out->data(), buf.data() + off, nb);
+    }
+    t_[name] = t;
+  }
+  return true;
+}
+
+const WTensor& WeightFile::get(const std::string& name) const {
+  auto it = t_.find(name);
+  if (it == t_.end()) throw std::runtime_error("weight tensor '" + name + "' missing");
+  return it->second;
+}
+
+// ----------------------------------------------------------------------------------- Arena
+Arena::~Arena() {
+  if (base_) cudaFree(base_);
+}
+cudaError_t Arena::reserve(size_t bytes) {
+  off_ = 0;
+  if (bytes <= cap_) return cudaSuccess;
+  if (base_) { cudaFree(base_); base_ = nullptr; cap_ = 0; }
+  bytes = (bytes + (size_t(1) << 26)) & ~((size_t(1) << 20) - 1);  // +64 MiB slack, MiB granularity
+  TT_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&base_), bytes));
+  cap_ = bytes;
+  return cudaSuccess;
+}
+void* Arena::alloc(size_t bytes) {
+  const size_t a = (off_ + 1023) & ~size_t(1023);
+  if (a + bytes > cap_) return nullptr;
+  off_ = a + bytes;
+  return base_ + a;
+}
+
+#define ARENA_GET(var, T, n)                                                       \
+  T* var = arena.get<T>(static_cast<size_t>(n));                                   \
+  if (!var) { set_error("arena exhausted (" #var ")"); return cudaErrorMemoryAllocation; }
+
+// ----------------------------------------------------------------------------------- CRAFT
+size_t DeviceCtx::craft_bytes(int B, int H, int W) const {
+  // bf16 elements per input pixel over every activation kept (no buffer reuse), see craft_forward
+  const double per_px = 32 + 64 + 64 + 64 / 4.0 + 128 / 4.0 + 128 / 4.0 + 128 / 16.0 + 3 * 256 / 16.0 + 256 / 64.0 +
+                        3 * 512 / 64.0 + 512 / 256.0 + 3 * 512 / 256.0 + 2 * 1024 / 256.0 + (512 + 256) / 256.0 +
+                        256 / 64.0 + (256 + 128) / 64.0 + 128 / 16.0 + (128 + 64) / 16.0 + 64 / 4.0 +
+                        (64 + 32) / 4.0 + 2 * 32 / 4.0;
+  const size_t px = static_cast<size_t>(B) * H * W;
+  return static_cast<size_t>(per_px * 2.0 * px) + px * 2 /*fp32 maps: 2 ch * 4 B / 4*/ + (64u << 10) * 64;
+}
+
+cudaError_t DeviceCtx::craft_forward(const uint8_t* in, int B, int H, int W, float** maps_out) {
+  using bf = __nv_bfloat16;
+  if (H % 32 || W % 32) { set_error("craft_forward: input must be padded to a multiple of 32"); return cudaErrorInvalidValue; }
+  const size_t px = static_cast<size_t>(B) * H * W;
+  const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16;
+  cudaStream_t s = stream;
+
+  auto conv = [&](const char* name, const bf* a, int Ca, const bf* b, int Cb, int h, int w, int taps, int dil, int cout,
+                  bool relu, bf* out) -> cudaError_t {
+    ConvProblem c;
+    c.batch = B; c.H = h; c.W = w;
+    c.src[0] = ConvSrc{a, Ca, Ca};
+    c.nsrc = 1;
+    if (b) { c.src[1] = ConvSrc{b, Cb, Cb}; c.nsrc = 2; }
+    c.taps = taps; c.dil = dil; c.Cout = cout;
+    c.weight = craft.bf(std::string(name) + ".w");
+    Epilogue e;
+    e.bias = craft.f32(std::string(name) + ".b");
+    e.act = relu ? ACT_RELU : ACT_NONE;
+    e.out = out; e.out_type = OUT_BF16; e.ldc = cout;
+    return conv_forward(c, e, s);
+  };
+#define CV(...) do { cudaError_t _e = conv(__VA_ARGS__); if (_e != cudaSuccess) return _e; } while (0)
+#define RUN(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
+
+  ARENA_GET(x0, bf, px * 32);
+  RUN(page_im2col(in, B, H, W, x0, s));
+  ARENA_GET(a1, bf, px * 64);
+  CV("c1_1", x0, 32, nullptr, 0, H, W, 1, 1, 64, true, a1);  // 3x3 conv as a K=32 GEMM over the im2col'd pixels
+  ARENA_GET(a2, bf, px * 64);
+  CV("c1_2", a1, 64, nullptr, 0, H, W, 9, 1, 64, true, a2);
+  ARENA_GET(p1, bf, px / 4 * 64);
+  RUN(maxpool2x2(a2, p1, B, H, W, 64, s));
+  ARENA_GET(b1, bf, px / 4 * 128);
+  CV("c2_1", p1, 64, nullptr, 0, H2, W2, 9, 1, 128, true, b1);
+  ARENA_GET(s1, bf, px / 4 * 128);  // relu2_2 (ReLU'd through upstream's in-place aliasing)
+  CV("c2_2", b1, 128, nullptr, 0, H2, W2, 9, 1, 128, true, s1);
+  ARENA_GET(p2, bf, px / 16 * 128);
+  RUN(maxpool2x2(s1, p2, B, H2, W2, 128, s));
+  ARENA_GET(c1, bf, px / 16 * 256);
+  CV("c3_1", p2, 128, nullptr, 0, H4, W4, 9, 1, 256, true, c1);
+  ARENA_GET(s2, bf, px / 16 * 256);  // relu3_2
+  CV("c3_2", c1, 256, nullptr, 0, H4, W4, 9, 1, 256, true, s2);
+  ARENA_GET(c3, bf, px / 16 * 256);
+  CV("c3_3", s2, 256, nullptr, 0, H4, W4, 9, 1, 256, true, c3);
+  ARENA_GET(p3, bf, px / 64 * 256);
+  RUN(maxpool2x2(c3, p3, B, H4, W4, 256, s));
+  ARENA_GET(d1, bf, px / 64 * 512);
+  CV("c4_1", p3, 256, nullptr, 0, H8, W8, 9, 1, 512, true, d1);
+  ARENA_GET(s3, bf, px / 64 * 512);  // "relu4_3" (really conv4_2)
+  CV("c4_2", d1, 512, nullptr, 0, H8, W8, 9, 1, 512, true, s3);
+  ARENA_GET(d3, bf, px / 64 * 512);
+  CV("c4_3", s3, 512, nullptr, 0, H8, W8, 9, 1, 512, true, d3);
+  ARENA_GET(p4, bf, px / 256 * 512);
+  RUN(maxpool2x2(d3, p4, B, H8, W8, 512, s));
+  ARENA_GET(e1, bf, px / 256 * 512);
+  CV("c5_1", p4, 512, nullptr, 0, H16, W16, 9, 1, 512, true, e1);
+  ARENA_GET(s4, bf, px / 256 * 512);  // "relu5_3": conv5_2 + BN, NOT ReLU'd (slice5 starts with a MaxPool)
+  CV("c5_2", e1, 512, nullptr, 0, H16, W16, 9, 1, 512, false, s4);
+  ARENA_GET(m5, bf, px / 256 * 512);
+  RUN(maxpool3x3s1(s4, m5, B, H16, W16, 512, s));
+  ARENA_GET(f6, bf, px / 256 * 1024);
+  CV("fc6", m5, 512, nullptr, 0, H16, W16, 9, 6, 1024, false, f6);
+  ARENA_GET(f7, bf, px / 256 * 1024);
+  CV("fc7", f6, 1024, nullptr, 0, H16, W16, 1, 1, 1024, false, f7);
+  // U-net head: double_conv(cat[y, skip]) with the concat fused into the 1x1 conv's K loop
+  ARENA_GET(u1a, bf, px / 256 * 512);
+  CV("up1a", f7, 1024, s4, 512, H16, W16, 1, 1, 512, true, u1a);
+  ARENA_GET(y1, bf, px / 256 * 256);
+  CV("up1b", u1a, 512, nullptr, 0, H16, W16, 9, 1, 256, true, y1);
+  ARENA_GET(y1u, bf, px / 64 * 256);
+  RUN(upsample2x(y1, y1u, B, H16, W16, 256, s));
+  ARENA_GET(u2a, bf, px / 64 * 256);
+  CV("up2a", y1u, 256, s3, 512, H8, W8, 1, 1, 256, true, u2a);
+  ARENA_GET(y2, bf, px / 64 * 128);
+  CV("up2b", u2a, 256, nullptr, 0, H8, W8, 9, 1, 128, true, y2);
+  ARENA_GET(y2u, bf, px / 16 * 128);
+  RUN(upsample2x(y2, y2u, B, H8, W8, 128, s));
+  ARENA_GET(u3a, bf, px / 16 * 128);
+  CV("up3a", y2u, 128, s2, 256, H4, W4, 1, 1, 128, true, u3a);
+  ARENA_GET(y3, bf, px / 16 * 64);
+  CV("up3b", u3a, 128, nullptr, 0, H4, W4, 9, 1, 64, true, y3);
+  ARENA_GET(y3u, bf, px / 4 * 64);
+  RUN(upsample2x(y3, y3u, B, H4, W4, 64, s));
+  ARENA_GET(u4a, bf, px / 4 * 64);
+  CV("up4a", y3u, 64, s1, 128, H2, W2, 1, 1, 64, true, u4a);
+  ARENA_GET(y4, bf, px / 4 * 32);
+  CV("up4b", u4a, 64, nullptr, 0, H2, W2, 9, 1, 32, true, y4);
+  ARENA_GET(k1, bf, px / 4 * 32);
+  CV("cls1", y4, 32, nullptr, 0, H2, W2, 9, 1, 32, true, k1);
+  ARENA_GET(k2, bf, px / 4 * 32);
+  CV("cls2", k1, 32, nullptr, 0, H2, W2, 9, 1, 32, true, k2);
+  ARENA_GET(maps, float, px / 4 * 2);
+  {
+    // cls3 (3x3 32->16 + ReLU) with cls4 (1x1 16->16 + ReLU) and cls5 (1x1 16->2) in its epilogue,
+    // writing the (H/2, W/2, 2) fp32 channels-last map the reference reads (tuatara.cpp:377-394)
+    ConvProblem c;
+    c.batch = B; c.H = H2; c.W = W2;
+    c.src[0] = ConvSrc{k2, 32, 32};
+    c.taps = 9; c.dil = 1; c.Cout = 16; c.BN = 16;
+    c.weight = craft.bf("cls3.w");
+    Epilogue e;
+    e.bias = craft.f32("cls3.b");
+    e.act = ACT_RELU;
+    e.out = maps; e.out_type = OUT_CLS_TAIL; e.ldc = 2;
+    e.tail = craft.f32("cls.tail");
+    RUN(conv_forward(c, e, s));
+  }
+  *maps_out = maps;
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------- PARSeq
+size_t DeviceCtx::parseq_bytes(int n) const {
+  const size_t M = static_cast<size_t>(n) * 128, D = pd.D;
+  size_t b = M * D * 4 + M * D * 2 + M * 3 * D * 2 + M * D * 2 + M * pd.mlp * 2 + M * D * 2 + M * 2 * D * 2;  // encoder
+  const size_t R = static_cast<size_t>(n) * pd.L;
+  b += R * 2 * D * 2 + R * 4 + R * D * (4 + 2 + 2 + 2 + 2) + R * pd.mlp * 2 + 2 * R * pd.n_cls_pad * 4 + 2 * R * 4;
+  return b + (1u << 20);
+}
+
+static cudaError_t lin(cudaStream_t s, const __nv_bfloat16* A, int lda, int M, int K, const __nv_bfloat16* W, int N,
+                       const float* bias, int act, const void* res, int res_type, int ldr, int res_mod, void* out,
+                       int out_type, int ldc) {
+  LinearProblem l;
+  l.A = A; l.lda = lda; l.M = M; l.K = K; l.W = W; l.N = N;
+  Epilogue e;
+  e.bias = bias; e.act = act; e.residual = res; e.res_type = res_type; e.ldr = ldr; e.res_mod = res_mod;
+  e.out = out; e.out_type = out_type; e.ldc = ldc;
+  return linear_forward(l, e, s);
+}
+
+cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const int* forced, float** logits_out,
+                                      int** ids_out) {
+  using bf = __nv_bfloat16;
+  const int D = pd.D, L = pd.L, M = n * 128, NC = pd.n_cls_pad;
+  cudaStream_t s = stream;
+  const WeightFile& w = parseq;
+
+  ARENA_GET(x, float, static_cast<size_t>(M) * D);       // fp32 residual stream
+  ARENA_GET(h, bf, static_cast<size_t>(M) * D);          // LayerNorm output / attention output
+  ARENA_GET(qkv, bf, static_cast<size_t>(M) * 3 * D);
+  ARENA_GET(att, bf, static_cast<size_t>(M) * D);
+  ARENA_GET(hid, bf, static_cast<size_t>(M) * pd.mlp);
+  ARENA_GET(mem, bf, static_cast<size_t>(M) * D);
+  ARENA_GET(mem_kv, bf, static_cast<size_t>(M) * 2 * D);
+
+  // patch embedding (Conv2d k=s=(4,8) as a K=96 GEMM) + bias + pos_embed
+  RUN(lin(s, patches, 96, M, 96, w.bf("pe.w"), D, w.f32("pe.b"), ACT_NONE, w.f32("pos"), RES_F32, D, 128, x, OUT_F32, D));
+  for (int i = 0; i < pd.depth; ++i) {
+    const std::string p = "b" + std::to_string(i) + ".";
+    RUN(layernorm(x, M, D, w.f32(p + "ln1.g"), w.f32(p + "ln1.b"), 1e-6f, h, nullptr, 0, s));
+    RUN(lin(s, h, D, M, D, w.bf(p + "qkv.w"), 3 * D, w.f32(p + "qkv.b"), ACT_NONE, nullptr, RES_NONE, 0, 0, qkv, OUT_BF16, 3 * D));
+    RUN(attention_enc(qkv, att, n, D, pd.enc_heads, s));
+    RUN(lin(s, att, D, M, D, w.bf(p + "proj.w"), D, w.f32(p + "proj.b"), ACT_NONE, x, RES_F32, D, 0, x, OUT_F32, D));
+    RUN(layernorm(x, M, D, w.f32(p + "ln2.g"), w.f32(p + "ln2.b"), 1e-6f, h, nullptr, 0, s));
+    RUN(lin(s, h, D, M, D, w.bf(p + "fc1.w"), pd.mlp, w.f32(p + "fc1.b"), ACT_GELU, nullptr, RES_NONE, 0, 0, hid, OUT_BF16, pd.mlp));
+    RUN(lin(s, hid, pd.mlp, M, pd.mlp, w.bf(p + "fc2.w"), D, w.f32(p + "fc2.b"), ACT_NONE, x, RES_F32, D, 0, x, OUT_F32, D));
+  }
+  RUN(layernorm(x, M, D, w.f32("enc.ln.g"), w.f32("enc.ln.b"), 1e-6f, mem, nullptr, 0, s));
+  // cross-attention K/V of the memory, once per crop (rows D.. of cross_attn.in_proj)
+  RUN(lin(s, mem, D, M, D, w.bf("dec.ca.in.w") + static_cast<size_t>(D) * D, 2 * D, w.f32("dec.ca.in.b") + D, ACT_NONE,
+          nullptr, RES_NONE, 0, 0, mem_kv, OUT_BF16, 2 * D));
+
+  // ---- decoder: 26 autoregressive steps + one cloze refinement
+  const int R = n * L;
+  ARENA_GET(kv_cache, bf, static_cast<size_t>(R) * 2 * D);
+  ARENA_GET(tokens, int, static_cast<size_t>(R));
+  ARENA_GET(t, float, static_cast<size_t>(R) * D);
+  ARENA_GET(hb, bf, static_cast<size_t>(R) * D);
+  ARENA_GET(qc, bf, static_cast<size_t>(R) * D);
+  ARENA_GET(ab, bf, static_cast<size_t>(R) * D);
+  ARENA_GET(ctx, bf, static_cast<size_t>(n) * D);
+  ARENA_GET(dh, bf, static_cast<size_t>(R) * pd.mlp);
+  ARENA_GET(logits_ar, float, static_cast<size_t>(R) * NC);
+  ARENA_GET(logits, float, static_cast<size_t>(R) * NC);
+  ARENA_GET(ids, int, static_cast<size_t>(R));
+  {
+    std::vector<int> init(static_cast<size_t>(R), pd.pad_id);
+    for (int c = 0; c < n; ++c) init[static_cast<size_t>(c) * L] = pd.bos_id;
+    TT_CUDA_TRY(cudaMemcpyAsync(tokens, init.data(), sizeof(int) * R, cudaMemcpyHostToDevice, s));
+    TT_CUDA_TRY(cudaStreamSynchronize(s));  // `init` is stack-owned
+  }
+  const float* posq = w.f32("posq");
+  auto stream_tail = [&](const DecoderStep& st, int rows, float* logits_dst, int ldl) -> cudaError_t {
+    // t = posq[p] + out_proj(self_attn); t += cross_attn(norm1(t)); t += mlp(norm2(t)); head(norm(t))
+    RUN(dec_self_attn(st, q_sa_table, kv_cache, tokens, pd.eos_id, ab, s));
+    RUN(lin(s, ab, D, rows, D, w.bf("dec.sa.out.w"), D, w.f32("dec.sa.out.b"), ACT_NONE, posq + static_cast<size_t>(st.p0) * D,
+            RES_F32, D, st.np, t, OUT_F32, D));
+    RUN(layernorm(t, rows, D, w.f32("dec.n1.g"), w.f32("dec.n1.b"), 1e-5f, hb, nullptr, 0, s));
+    RUN(lin(s, hb, D, rows, D, w.bf("dec.ca.in.w"), D, w.f32("dec.ca.in.b"), ACT_NONE, nullptr, RES_NONE, 0, 0, qc, OUT_BF16, D));
+    RUN(dec_cross_attn(st, qc, mem_kv, ab, s));
+    RUN(lin(s, ab, D, rows, D, w.bf("dec.ca.out.w"), D, w.f32("dec.ca.out.b"), ACT_NONE, t, RES_F32, D, 0, t, OUT_F32, D));
+    RUN(layernorm(t, rows, D, w.f32("dec.n2.g"), w.f32("dec.n2.b"), 1e-5f, hb, nullptr, 0, s));
+    RUN(lin(s, hb, D, rows, D, w.bf("dec.l1.w"), pd.mlp, w.f32("dec.l1.b"), ACT_GELU, nullptr, RES_NONE, 0, 0, dh, OUT_BF16, pd.mlp));
+    RUN(lin(s, dh, pd.mlp, rows, pd.mlp, w.bf("dec.l2.w"), D, w.f32("dec.l2.b"), ACT_NONE, t, RES_F32, D, 0, t, OUT_F32, D));
+    RUN(layernorm(t, rows, D, w.f32("dec.norm.g"), w.f32("dec.norm.b"), 1e-5f, hb, nullptr, 0, s));
+    RUN(lin(s, hb, D, rows, D, w.bf("head.w"), NC, w.f32("head.b"), ACT_NONE, nullptr, RES_NONE, 0, 0, logits_dst, OUT_F32, ldl));
+    return cudaSuccess;
+  };
+  for (int i = 0; i < L; ++i) {
+    // content K/V of position i joins the cache (rows D.. of self_attn.in_proj = K | V)
+    RUN(dec_context(tokens, w.f32("embed"), posq, w.f32("dec.nc.g"), w.f32("dec.nc.b"), 1e-5f, i, n, D, L, ctx, s));
+    RUN(lin(s, ctx, D, n, D, w.bf("dec.sa.in.w") + static_cast<size_t>(D) * D, 2 * D, w.f32("dec.sa.in.b") + D, ACT_NONE,
+            nullptr, RES_NONE, 0, 0, kv_cache + static_cast<size_t>(i) * 2 * D, OUT_BF16, L * 2 * D));
+    DecoderStep st{n, D, pd.dec_heads, L, i, 1, 0};
+    RUN(stream_tail(st, n, logits_ar + static_cast<size_t>(i) * NC, L * NC));
+    if (i + 1 < L)
+      RUN(argmax_rows(logits_ar + static_cast<size_t>(i) * NC, n, pd.n_cls, L * NC, nullptr, 0, tokens + i + 1, L,
+                      forced ? forced + i : nullptr, L - 1, s));
+  }
+  DecoderStep st{n, D, pd.dec_heads, L, 0, L, 1};
+  RUN(stream_tail(st, R, logits, NC));
+  RUN(argmax_rows(logits, R, pd.n_cls, NC, ids, 1, nullptr, 0, nullptr, 0, s));
+  *logits_out = logits;
+  *ids_out = ids;
+  return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------- DeviceCtx
+DeviceCtx::~DeviceCtx() {
+  cudaSetDevice(device);
+  if (q_sa_table) cudaFree(q_sa_table);
+  post_workspace_free(&post);
+  if (pinned) cudaFreeHost(pinned);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+cudaError_t DeviceCtx::ensure_pinned(size_t bytes) {
+  if (bytes <= pinned_bytes) return cudaSuccess;
+  if (pinned) cudaFreeHost(pinned);
+  pinned = nullptr;
+  pinned_bytes = 0;
+  TT_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&pinned), bytes));
+  pinned_bytes = bytes;
+  return cudaSuccess;
+}
+
+cudaError_t DeviceCtx::init(const std::string& dir) {
+  TT_CUDA_TRY(cudaSetDevice(device));
+  TT_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  std::vector<int> meta;
+  if (!craft.load(dir + "/craft.ttw")) return cudaErrorInvalidValue;
+  if (!parseq.load(dir + "/parseq.ttw", &meta)) return cudaErrorInvalidValue;
+  if (meta.size() >= 8) {
+    pd.D = meta[0]; pd.depth = meta[1]; pd.enc_heads = meta[2]; pd.dec_heads = meta[3]; pd.mlp = meta[4];
+    pd.n_cls = meta[5]; pd.L = meta[6]; pd.n_tok = meta[7];
+    pd.n_cls_pad = (pd.n_cls + 15) / 16 * 16;
+    pd.eos_id = 0; pd.bos_id = pd.n_tok - 2; pd.pad_id = pd.n_tok - 1;
+  }
+  if (pd.D != 384) { set_error("only PARSeq-base (embed_dim 384) is built in this round"); return cudaErrorInvalidValue; }
+  // self-attention queries: W_q LN_q(pos_queries) + b_q, identical for every crop
+  TT_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q_sa_table), sizeof(float) * pd.L * pd.D));
+  TT_CUDA_TRY(arena.reserve(1u << 20));
+  arena.reset();
+  __nv_bfloat16* qn = arena.get<__nv_bfloat16>(static_cast<size_t>(pd.L) * pd.D);
+  RUN(layernorm(parseq.f32("posq"), pd.L, pd.D, parseq.f32("dec.nq.g"), parseq.f32("dec.nq.b"), 1e-5f, qn, nullptr, 0, stream));
+  RUN(lin(stream, qn, pd.D, pd.L, pd.D, parseq.bf("dec.sa.in.w"), pd.D, parseq.f32("dec.sa.in.b"), ACT_NONE, nullptr,
+          RES_NONE, 0, 0, q_sa_table, OUT_F32, pd.D));
+  TT_CUDA_TRY(cudaStreamSynchronize(stream));
+  return cudaSuccess;
+}
+
+}  // namespace tt

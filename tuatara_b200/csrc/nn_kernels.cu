@@ -1,0 +1,530 @@
+// Non-GEMM kernels of CRAFT and PARSeq (see nn_kernels.cuh).  They stand in for the ATen ops the
+// reference reaches through TorchScript (tuatara.cpp:376, :307): max_pool2d, upsample_bilinear2d,
+// layer_norm, scaled-dot-product attention, embedding, argmax.
+#include "nn_kernels.cuh"
+
+#include <cuda.h>
+#include <math.h>
+
+#include "common.h"
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+
+namespace tt {
+
+namespace {
+
+__device__ __forceinline__ uint4 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st8(__nv_bfloat16* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
+  uint4 r;
+  const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* z = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) z[i] = __hmax2(x[i], y[i]);
+  return r;
+}
+__device__ __forceinline__ void unpack8(uint4 v, float f[8]) {
+  const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __low2float(x[i]); f[2 * i + 1] = __high2float(x[i]); }
+}
+__device__ __forceinline__ uint4 pack8(const float f[8]) {
+  uint4 r;
+  __nv_bfloat162* z = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) z[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return r;
+}
+
+// ------------------------------------------------------------------------------- CRAFT aux
+__global__ void k_maxpool2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                           int C) {
+  const int Ho = H / 2, Wo = W / 2, C8 = C / 8;
+  const long long total = static_cast<long long>(B) * Ho * Wo * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C8);
+    long long t = i / C8;
+    const int x = static_cast<int>(t % Wo); t /= Wo;
+    const int y = static_cast<int>(t % Ho);
+    const int b = static_cast<int>(t / Ho);
+    const __nv_bfloat16* p = in + ((static_cast<long long>(b) * H + 2 * y) * W + 2 * x) * C + c * 8;
+    const uint4 v = max8(max8(ld8(p), ld8(p + C)), max8(ld8(p + static_cast<long long>(W) * C), ld8(p + static_cast<long long>(W) * C + C)));
+    st8(out + ((static_cast<long long>(b) * Ho + y) * Wo + x) * C + c * 8, v);
+  }
+}
+
+__global__ void k_maxpool3(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                           int C) {
+  const int C8 = C / 8;
+  const long long total = static_cast<long long>(B) * H * W * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C8);
+    long long t = i / C8;
+    const int x = static_cast<int>(t % W); t /= W;
+    const int y = static_cast<int>(t % H);
+    const int b = static_cast<int>(t / H);
+    const __nv_bfloat16* base = in + static_cast<long long>(b) * H * W * C + c * 8;
+    uint4 v = ld8(base + (static_cast<long long>(y) * W + x) * C);
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = y + dy, xx = x + dx;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;  // padding is -inf for max pooling
+        v = max8(v, ld8(base + (static_cast<long long>(yy) * W + xx) * C));
+      }
+    st8(out + i * 8, v);
+  }
+}
+
+__global__ void k_upsample2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                            int C) {
+  const int Ho = 2 * H, Wo = 2 * W, C8 = C / 8;
+  const long long total = static_cast<long long>(B) * Ho * Wo * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C8);
+    long long t = i / C8;
+    const int x = static_cast<int>(t % Wo); t /= Wo;
+    const int y = static_cast<int>(t % Ho);
+    const int b = static_cast<int>(t / Ho);
+    // area_pixel_compute_source_index(scale 0.5, align_corners=False): max(0, (dst + 0.5) * 0.5 - 0.5)
+    const float sy = fmaxf(0.f, (y + 0.5f) * 0.5f - 0.5f), sx = fmaxf(0.f, (x + 0.5f) * 0.5f - 0.5f);
+    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    const __nv_bfloat16* base = in + static_cast<long long>(b) * H * W * C + c * 8;
+    float a[8], bb[8], cc[8], d[8], o[8];
+    unpack8(ld8(base + (static_cast<long long>(y0) * W + x0) * C), a);
+    unpack8(ld8(base + (static_cast<long long>(y0) * W + x1) * C), bb);
+    unpack8(ld8(base + (static_cast<long long>(y1) * W + x0) * C), cc);
+    unpack8(ld8(base + (static_cast<long long>(y1) * W + x1) * C), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      o[k] = (1.f - ly) * ((1.f - lx) * a[k] + lx * bb[k]) + ly * ((1.f - lx) * cc[k] + lx * d[k]);
+    st8(out + i * 8, pack8(o));
+  }
+}
+
+int grid_for(long long total, int block) {
+  const long long g = (total + block - 1) / block;
+  return static_cast<int>(g < 148LL * 16 ? (g > 0 ? g : 1) : 148LL * 16);
+}
+
+// ------------------------------------------------------------------------------- LayerNorm
+template <int PER_LANE>
+__global__ void k_layernorm(const float* __restrict__ x, int rows, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ ob,
+                            float* __restrict__ of, int rows_mod) {
+  constexpr int D = PER_LANE * 32;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + static_cast<long long>(rows_mod > 0 ? row % rows_mod : row) * D;
+  float v[PER_LANE];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE / 4; ++i) {
+    const float4 t = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    sum += t.x + t.y + t.z + t.w;
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / D;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) { const float d = v[i] - mean; var += d * d; }
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / D + eps);
+#pragma unroll
+  for (int i = 0; i < PER_LANE / 4; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+    const float4 b = *reinterpret_cast<const float4*>(beta + col);
+    const float o0 = (v[4 * i] - mean) * rstd * g.x + b.x, o1 = (v[4 * i + 1] - mean) * rstd * g.y + b.y;
+    const float o2 = (v[4 * i + 2] - mean) * rstd * g.z + b.z, o3 = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
+    if (ob != nullptr) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0);
+      u.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(ob + static_cast<long long>(row) * D + col) = u;
+    }
+    if (of != nullptr) *reinterpret_cast<float4*>(of + static_cast<long long>(row) * D + col) = make_float4(o0, o1, o2, o3);
+  }
+}
+
+// ------------------------------------------------------------------------ encoder attention
+// grid (heads, crops), 128 threads.  smem (1024-aligned): [Q 16K][K 16K][V 16K]; P (bf16 128x128,
+// two 64-key swizzle atoms = 32K) overwrites Q|K once S = QK^T has been consumed.
+struct AttnCtl {
+  uint64_t bar_load, bar_s, bar_o;
+  uint32_t tmem_base;
+};
+constexpr int kAttnSmem = 3 * 16384 + 1024 + 64;
+
+__global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtensorMap tm_qkv,
+                                                  __nv_bfloat16* __restrict__ out, int D, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 16384;
+  uint8_t* sV = smem + 32768;
+  uint8_t* sP = smem;  // aliases Q|K
+  AttnCtl* ctl = reinterpret_cast<AttnCtl*>(smem + 49152);
+  const int head = blockIdx.x, crop = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tm_qkv);
+    ptx::mbar_init(&ctl->bar_load, 1);
+    ptx::mbar_init(&ctl->bar_s, 1);
+    ptx::mbar_init(&ctl->bar_o, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) ptx::tmem_alloc(&ctl->tmem_base, 128);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = ctl->tmem_base;
+
+  if (tid == 0) {
+    ptx::mbar_arrive_expect_tx(&ctl->bar_load, 3 * 16384);
+    ptx::tma_load_2d(sQ, &tm_qkv, &ctl->bar_load, head * 64, crop * 128);
+    ptx::tma_load_2d(sK, &tm_qkv, &ctl->bar_load, D + head * 64, crop * 128);
+    ptx::tma_load_2d(sV, &tm_qkv, &ctl->bar_load, 2 * D + head * 64, crop * 128);
+    ptx::mbar_wait(&ctl->bar_load, 0);
+    ptx::tc_fence_after();
+    // S[128 q][128 k] = Q K^T : both operands K-major over the 64 head dims
+    const uint32_t idesc = ptx::make_idesc_bf16(128, 128);
+    const uint32_t qa = ptx::smem_u32(sQ), ka = ptx::smem_u32(sK);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      ptx::mma_bf16(tmem, ptx::make_smem_desc(qa + k * 32, 128), ptx::make_smem_desc(ka + k * 32, 128), idesc, k != 0);
+    ptx::mma_commit(&ctl->bar_s);
+  }
+  ptx::mbar_wait(&ctl->bar_s, 0);
+  ptx::tc_fence_after();
+
+  // softmax over this thread's row (row == TMEM lane == tid)
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  float mx = -INFINITY;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    uint32_t raw[16];
+    ptx::tmem_ld16(t_row + ch * 16, raw);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+  }
+  float sum = 0.f;
+  const int r = tid;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    uint32_t raw[16];
+    ptx::tmem_ld16(t_row + ch * 16, raw);
+    ptx::tmem_ld_wait();
+    float p[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      p[i] = exp2f((__uint_as_float(raw[i]) - mx) * scale_log2e);
+      sum += p[i];
+    }
+    // P as the A operand of the second MMA: K-major SWIZZLE_128B, keys [64b, 64b+64) in atom block b
+    uint8_t* blk = sP + (ch >> 2) * 16384 + r * 128;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int chunk = ((ch & 3) * 2 + h) ^ (r & 7);
+      uint4 u;
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(p[8 * h + 0], p[8 * h + 1]);
+      __nv_bfloat162 t1 = __floats2bfloat162_rn(p[8 * h + 2], p[8 * h + 3]);
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(p[8 * h + 4], p[8 * h + 5]);
+      __nv_bfloat162 t3 = __floats2bfloat162_rn(p[8 * h + 6], p[8 * h + 7]);
+      u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
+      u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
+      *reinterpret_cast<uint4*>(blk + chunk * 16) = u;
+    }
+  }
+  // generic-proxy smem writes -> visible to the tensor core (async proxy); all S reads retired
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    ptx::tc_fence_after();
+    // O[128 q][64 d] = P V : A = P (K-major over keys), B = V as loaded: rows = keys, 64 dims contiguous
+    // == MN-major SWIZZLE_128B, one 1024-byte atom per 8 keys (SBO = 1024), 16 keys per MMA.
+    const uint32_t idesc = ptx::make_idesc_bf16(128, 64) | (1u << 16);  // b_major = MN
+    const uint32_t pa = ptx::smem_u32(sP), va = ptx::smem_u32(sV);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint64_t da = ptx::make_smem_desc(pa + (k >> 2) * 16384 + (k & 3) * 32, 128);
+      const uint64_t db = ptx::make_smem_desc(va + k * 2048, 128);
+      ptx::mma_bf16(tmem, da, db, idesc, k != 0);
+    }
+    ptx::mma_commit(&ctl->bar_o);
+  }
+  ptx::mbar_wait(&ctl->bar_o, 0);
+  ptx::tc_fence_after();
+  const float inv = 1.f / sum;
+  __nv_bfloat16* orow = out + (static_cast<long long>(crop) * 128 + r) * D + head * 64;
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t raw[16];
+    ptx::tmem_ld16(t_row + ch * 16, raw);
+    ptx::tmem_ld_wait();
+    float o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(raw[i]) * inv;
+    st8(orow + ch * 16, pack8(o));
+    st8(orow + ch * 16 + 8, pack8(o + 8));
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 128);
+  }
+}
+
+// ------------------------------------------------------------------------- decoder kernels
+// one warp per crop: content embedding -> LayerNorm -> bf16
+template <int PER_LANE>
+__global__ void k_dec_context(const int* __restrict__ tokens, const float* __restrict__ embed,
+                              const float* __restrict__ posq, const float* __restrict__ g, const float* __restrict__ b,
+                              float eps, int pos, int n, int L, __nv_bfloat16* __restrict__ out) {
+  constexpr int D = PER_LANE * 32;
+  const int crop = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (crop >= n) return;
+  const int tok = tokens[crop * L + pos];
+  const float* e = embed + static_cast<long long>(tok) * D;
+  float v[PER_LANE];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const int col = i * 32 + lane;
+    v[i] = e[col] + (pos > 0 ? posq[(pos - 1) * D + col] : 0.f);
+    sum += v[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / D;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) { const float d = v[i] - mean; var += d * d; }
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / D + eps);
+#pragma unroll
+  for (int i = 0; i < PER_LANE; ++i) {
+    const int col = i * 32 + lane;
+    out[static_cast<long long>(crop) * D + col] = __float2bfloat16((v[i] - mean) * rstd * g[col] + b[col]);
+  }
+}
+
+// grid (np, crops), block = heads*32 threads: warp = head, lane = head dim (32)
+__global__ void k_dec_self_attn(DecoderStep st, const float* __restrict__ q_table,
+                                const __nv_bfloat16* __restrict__ kv, const int* __restrict__ tokens, int eos_id,
+                                __nv_bfloat16* __restrict__ out) {
+  const int pi = blockIdx.x, crop = blockIdx.y;
+  const int p = st.p0 + pi;
+  const int head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = st.D, L = st.L;
+  const float q = q_table[p * D + head * 32 + lane] * 0.17677669529663687f;  // 1/sqrt(32)
+  const __nv_bfloat16* kbase = kv + static_cast<long long>(crop) * L * 2 * D + head * 32 + lane;
+  // key j allowed?  AR: j <= p.  refine: j != p+1 and no EOS among tokens[1..j]
+  int first_eos = L;  // first j >= 1 with tokens[j] == eos
+  if (st.refine) {
+    const int t = (lane + 1 < L) ? tokens[crop * L + lane + 1] : -1;  // L <= 33
+    const unsigned m = __ballot_sync(0xffffffffu, t == eos_id);
+    if (m) first_eos = __ffs(m);  // lane l holds token l+1
+  }
+  float my_score = -INFINITY;  // lane j keeps the score of key j
+  const int nkeys = st.refine ? L : p + 1;
+  for (int j = 0; j < nkeys; ++j) {
+    const bool ok = st.refine ? (j != p + 1 && j < first_eos) : true;
+    if (!ok) continue;  // warp-uniform
+    float d = q * __bfloat162float(kbase[static_cast<long long>(j) * 2 * D]);
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == j) my_score = d;
+  }
+  float mx = my_score;
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float e = (my_score == -INFINITY) ? 0.f : __expf(my_score - mx);
+  float sum = e;
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float pr = e / sum;
+  float acc = 0.f;
+  for (int j = 0; j < nkeys; ++j) {
+    const float pj = __shfl_sync(0xffffffffu, pr, j);
+    if (pj != 0.f) acc += pj * __bfloat162float(kbase[static_cast<long long>(j) * 2 * D + D]);
+  }
+  out[(static_cast<long long>(crop) * st.np + pi) * D + head * 32 + lane] = __float2bfloat16(acc);
+}
+
+// grid (np, crops), block = heads*32: warp = head; 128 memory keys, 4 per lane for the scores
+__global__ void k_dec_cross_attn(DecoderStep st, const __nv_bfloat16* __restrict__ q,
+                                 const __nv_bfloat16* __restrict__ mem_kv, __nv_bfloat16* __restrict__ out) {
+  const int pi = blockIdx.x, crop = blockIdx.y;
+  const int head = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = st.D;
+  const long long row = static_cast<long long>(crop) * st.np + pi;
+  // the head's 32 query dims, one per lane, broadcast by shuffle
+  const float qd = __bfloat162float(q[row * D + head * 32 + lane]) * 0.17677669529663687f;
+  const __nv_bfloat16* kv = mem_kv + static_cast<long long>(crop) * 128 * 2 * D + head * 32;
+  float sc[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int key = t * 32 + lane;
+    const uint4* kp = reinterpret_cast<const uint4*>(kv + static_cast<long long>(key) * 2 * D);
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float f[8];
+      unpack8(__ldg(kp + c), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc += __shfl_sync(0xffffffffu, qd, c * 8 + i) * f[i];
+    }
+    sc[t] = acc;
+  }
+  float mx = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) { sc[t] = __expf(sc[t] - mx); sum += sc[t]; }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  float acc = 0.f;  // lane = output dim
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    for (int l = 0; l < 32; ++l) {
+      const float pj = __shfl_sync(0xffffffffu, sc[t], l);
+      acc += pj * __bfloat162float(kv[static_cast<long long>(t * 32 + l) * 2 * D + D + lane]);
+    }
+  }
+  out[row * D + head * 32 + lane] = __float2bfloat16(acc * inv);
+}
+
+__global__ void k_argmax(const float* __restrict__ logits, int rows, int n_cls, int ld, int* __restrict__ ids,
+                         int ids_stride, int* __restrict__ next, int next_stride, const int* __restrict__ forced,
+                         int forced_stride) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* l = logits + static_cast<long long>(row) * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < n_cls; c += 32) {
+    const float v = l[c];
+    if (v > best) { best = v; bi = c; }  // strictly greater: first max per lane
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }  // ties -> lowest index (at::max on CPU)
+  }
+  if (lane == 0) {
+    if (ids != nullptr) ids[static_cast<long long>(row) * ids_stride] = bi;
+    if (next != nullptr) next[static_cast<long long>(row) * next_stride] = forced ? forced[static_cast<long long>(row) * forced_stride] : bi;
+  }
+}
+
+__global__ void k_patchify(const uint8_t* __restrict__ crops, int n, __nv_bfloat16* __restrict__ out) {
+  const int dy = blockIdx.x, b = blockIdx.y, dx = threadIdx.x;
+  const uint8_t* p = crops + ((static_cast<size_t>(b) * 32 + dy) * 128 + dx) * 3;
+  const size_t row = static_cast<size_t>(b) * 128 + (dy >> 2) * 16 + (dx >> 3);
+  __nv_bfloat16* o = out + row * 96 + (dy & 3) * 8 + (dx & 7);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c * 32] = __float2bfloat16(static_cast<float>(p[c]));
+}
+
+}  // namespace
+
+cudaError_t maxpool2x2(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);
+  k_maxpool2<<<grid_for(total, 256), 256, 0, s>>>(in, out, B, H, W, C);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t maxpool3x3s1(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * H * W * (C / 8);
+  k_maxpool3<<<grid_for(total, 256), 256, 0, s>>>(in, out, B, H, W, C);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
+  k_upsample2<<<grid_for(total, 256), 256, 0, s>>>(in, out, B, H, W, C);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t layernorm(const float* x, int rows, int D, const float* gamma, const float* beta, float eps,
+                      __nv_bfloat16* ob, float* of, int rows_mod, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  const int grid = (rows + 7) / 8;
+  if (D == 384) k_layernorm<12><<<grid, 256, 0, s>>>(x, rows, gamma, beta, eps, ob, of, rows_mod);
+  else { set_error("layernorm: unsupported width (PARSeq-base, D = 384, only)"); return cudaErrorInvalidValue; }
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t attention_enc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int crops, int D, int heads, cudaStream_t s) {
+  if (crops <= 0) return cudaSuccess;
+  if (D != heads * 64) { set_error("attention_enc: head dim must be 64"); return cudaErrorInvalidValue; }
+  CUtensorMap tm;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(3 * D), static_cast<cuuint64_t>(crops) * 128};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(3 * D) * 2};
+  const cuuint32_t box[2] = {64, 128};
+  if (!make_tmap_bf16(&tm, qkv, 2, dims, strides, box, 128)) return cudaErrorInvalidValue;
+  TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(k_attn_enc), kAttnSmem));
+  const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
+  k_attn_enc<<<dim3(heads, crops), 128, kAttnSmem, s>>>(tm, out, D, scale_log2e);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t dec_context(const int* tokens, const float* embed, const float* posq, const float* g, const float* b,
+                        float eps, int pos, int n, int D, int L, __nv_bfloat16* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  if (D != 384) { set_error("dec_context: unsupported width"); return cudaErrorInvalidValue; }
+  k_dec_context<12><<<(n + 7) / 8, 256, 0, s>>>(tokens, embed, posq, g, b, eps, pos, n, L, out);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t dec_self_attn(const DecoderStep& st, const float* q_table, const __nv_bfloat16* kv, const int* tokens,
+                          int eos_id, __nv_bfloat16* out, cudaStream_t s) {
+  if (st.n_crops <= 0) return cudaSuccess;
+  if (st.D != st.heads * 32 || st.L > 32) { set_error("dec_self_attn: head dim must be 32, L <= 32"); return cudaErrorInvalidValue; }
+  k_dec_self_attn<<<dim3(st.np, st.n_crops), st.heads * 32, 0, s>>>(st, q_table, kv, tokens, eos_id, out);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t dec_cross_attn(const DecoderStep& st, const __nv_bfloat16* q, const __nv_bfloat16* mem_kv,
+                           __nv_bfloat16* out, cudaStream_t s) {
+  if (st.n_crops <= 0) return cudaSuccess;
+  if (st.D != st.heads * 32) { set_error("dec_cross_attn: head dim must be 32"); return cudaErrorInvalidValue; }
+  k_dec_cross_attn<<<dim3(st.np, st.n_crops), st.heads * 32, 0, s>>>(st, q, mem_kv, out);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t argmax_rows(const float* logits, int rows, int n_cls, int ld, int* ids, int ids_stride, int* next,
+                        int next_stride, const int* forced, int forced_stride, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  k_argmax<<<(rows + 7) / 8, 256, 0, s>>>(logits, rows, n_cls, ld, ids, ids_stride, next, next_stride, forced,
+                                          forced_stride);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t patchify_u8(const uint8_t* crops, int n, __nv_bfloat16* out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_patchify<<<dim3(32, n), 128, 0, s>>>(crops, n, out);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+}  // namespace tt
