@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the Tuatara OCR hot path on B200 (BASELINE.json metric: pages/sec end-to-end,
+synthetic 1280x1280 pages, 1/2/4/8 GPUs).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
+
+One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE for N > 1).  A *step* is one pass
+of the whole path (CRAFT -> post-process -> crop/resize -> PARSeq -> decode) over this rank's batch
+of synthetic pages; pages are independent, so ranks share nothing (weak scaling, no collective on
+the data path; torch.distributed is used only for the barrier and the max-over-ranks of the time).
+
+Workload: uint8 1280x1280x3 pages, 300 words each, reference defaults
+(canvas 1024 -> CRAFT input 1024^2 -> 512^2 score maps).  Random-init weights give near-constant
+score maps, so after CRAFT has run in full its output is overwritten with the deterministic
+synthetic score map of the page (300 components -> 300 boxes -> 300 crops); the override is a
+2 MiB device-to-device copy per page inside the timed region.
+
+`value`  : pages/s with pages + override maps already resident in HBM.
+`e2e`    : pages/s through the C ABI with pages in pinned HOST memory (H2D of the pages, D2H of the
+           results inside the timed region).
+`roofline`: the dominant kernel (tcgen05 GEMM / implicit-GEMM conv), algorithmic FLOPs / summed
+           per-launch CUDA-event time over the timed region vs the measured sustained bf16 peak.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORDS = 300
+PAGE = 1280
+# SURVEY.md 8d / BASELINE.md section 3: algorithmic work per unit
+CRAFT_GFLOP_PER_PAGE = 746.0
+PARSEQ_GFLOP_PER_CROP = 6.05
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while a timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+        self.f.flush()
+        rows = [l.split(",") for l in Path(self.f.name).read_text().splitlines() if l.count(",") >= 7]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def ensure_weights():
+    """Seeded random-init weights of the named architectures (no checkpoints offline)."""
+    from tuatara_b200 import weights
+
+    return weights.export_random(ROOT / "tests" / "_cache" / "weights_bench_seed0", seed=0)
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+def cpu_pipeline_sample(n_pages: int, faithful: bool = True):
+    """The reference algorithm (oracle: torch CPU + cv2, the native kernels the reference links) on
+    `n_pages` synthetic pages with models pre-loaded.  Returns (seconds, pages, threads)."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import tuatara_ref as R
+    from oracle.models import make_craft, make_parseq
+    from tuatara_b200 import synth
+
+    craft, parseq = make_craft(0), make_parseq("base", 0)
+    pages = [synth.synth_page(i) for i in range(n_pages)]
+    maps = [synth.synth_score_maps(i) for i in range(n_pages)]
+
+    if faithful:
+        # tuatara.cpp:452-475: chunks of 4 crops pulled by 6 threads from a queue
+        pool = ThreadPoolExecutor(6)
+
+        def run_parseq(_model, crops_u8, chunk_size=4):
+            t = torch.from_numpy(crops_u8).permute(0, 3, 1, 2).to(torch.float32).div(255.0)
+            chunks = [t[i:i + 4] for i in range(0, t.shape[0], 4)]
+            return torch.cat(list(pool.map(parseq, chunks)), 0)
+
+        R.run_parseq = run_parseq
+    t0 = time.perf_counter()
+    for img, m in zip(pages, maps):
+        out = R.image_to_data(img.copy(), craft, parseq, score_override=(m[..., 0], m[..., 1]))
+        assert len(out) == WORDS
+    return time.perf_counter() - t0, n_pages, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import torch
+
+    times = []
+    t_start = time.perf_counter()
+    budget = 240.0
+    done = 0
+    for i in range(args.warmup + args.steps):
+        sec, n, threads = cpu_pipeline_sample(1)
+        if i >= args.warmup:
+            times.append(sec)
+            done += 1
+        if time.perf_counter() - t_start > budget and done >= 1:
+            break
+    sec = sum(times) / len(times)
+    val = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": "pages/sec end-to-end", "value": val, "unit": "pages/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "synthetic 1280x1280 pages, 300 words/page, canvas 1024, score-map override",
+                   "pages_per_step": 1, "note": "reference algorithm via torch CPU + cv2 (oracle/), models pre-loaded, "
+                   "PARSeq in chunks of 4 on 6 threads like tuatara.cpp:452-475"},
+        "cpu_baseline": {"value": val, "unit": "pages/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"1 page (300 crops) per step, {done} steps, torch threads {torch.get_num_threads()}"},
+        "e2e": {"value": val, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ multi-rank host logic
+def rank_page_indices(rank: int, pages_per_gpu: int) -> list[int]:
+    """Pages are independent units: rank r owns pages [r*n, (r+1)*n) of the synthetic set (weak scaling)."""
+    return list(range(rank * pages_per_gpu, (rank + 1) * pages_per_gpu))
+
+
+def max_over_ranks(ms: float, world: int, device) -> float:
+    """The job's time is the slowest rank's device time."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def job_throughput(pages_per_gpu: int, world: int, steps: int, ms_max: float) -> float:
+    """Whole-job pages/s: all ranks' pages over the max-over-ranks time."""
+    return pages_per_gpu * world * steps / (ms_max / 1e3)
+
+
+# ------------------------------------------------------------------------------------ native arm
+def run_native(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import tuatara_b200 as tb
+    from tuatara_b200 import _native, build, synth
+
+    if not _native.LIB_PATH.exists():
+        build.build()
+    lib = tb.lib()
+    wdir = ensure_weights() if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    wdir = ensure_weights()
+    cfg = tb.default_config()
+    cfg.max_batch_pages = args.batch_pages
+    eng = tb.Engine(wdir, devices=[local_rank], cfg=cfg)
+    stream = torch.cuda.ExternalStream(lib.tt_engine_stream(eng._h, 0), device=torch.device("cuda", local_rank))
+
+    n = args.pages_per_gpu
+    mine = rank_page_indices(rank, n)
+    pages_np = [synth.synth_page(i) for i in mine]
+    maps_np = [synth.synth_score_maps(i) for i in mine]
+    pages_dev = [torch.from_numpy(p).cuda() for p in pages_np]
+    maps_dev = [torch.from_numpy(m).cuda() for m in maps_np]
+    pages_pin = [torch.from_numpy(p).pin_memory() for p in pages_np]
+
+    def make_call(tensors, on_dev):
+        arr = (_native.tt_image * n)(*[_native.tt_image(t.data_ptr(), PAGE, PAGE, 3, PAGE * 3) for t in tensors])
+        ptrs = (C.c_void_p * n)(*[m.data_ptr() for m in maps_dev])
+        opt = _native.tt_ocr_options(int(on_dev), 1, ptrs)
+
+        def call():
+            res = C.POINTER(_native.tt_result)()
+            tb.check(lib.tt_ocr_pages_ex(eng._h, arr, n, C.byref(opt), C.byref(res)), "tt_ocr_pages_ex")
+            items = sum(res.contents.pages[i].n_items for i in range(res.contents.n_pages))
+            lib.tt_result_free(res)
+            return items
+        call.keep = (arr, ptrs, opt)
+        return call
+
+    step_dev = make_call(pages_dev, True)
+    step_host = make_call(pages_pin, False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, steps, profile=False):
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        l0 = tb.launch_count()
+        h0, d0 = C.c_ulonglong(), C.c_ulonglong()
+        lib.tt_io_bytes(C.byref(h0), C.byref(d0))
+        if profile:
+            lib.tt_profile_enable(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        items = 0
+        for _ in range(steps):
+            items += step()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = None
+        if profile:
+            lib.tt_profile_enable(0)
+            pm, pf, pl = C.c_double(), C.c_double(), C.c_ulonglong()
+            lib.tt_profile_collect(C.byref(pm), C.byref(pf), C.byref(pl))
+            prof = (pm.value, pf.value, pl.value)
+        clocks = sampler.stop()
+        h1, d1 = C.c_ulonglong(), C.c_ulonglong()
+        lib.tt_io_bytes(C.byref(h1), C.byref(d1))
+        assert items == steps * n * WORDS, f"expected {steps * n * WORDS} items, got {items}"
+        return dict(ms=max_over_ranks(ms, world, "cuda"), launches=tb.launch_count() - l0, h2d=(h1.value - h0.value) / steps,
+                    d2h=(d1.value - d0.value) / steps, prof=prof, clocks=clocks)
+
+    for _ in range(args.warmup):
+        step_dev()
+    r_dev = timed(step_dev, args.steps, profile=True)
+    step_host()
+    r_host = timed(step_host, args.steps)
+
+    value = job_throughput(n, world, args.steps, r_dev["ms"])
+    e2e = job_throughput(n, world, args.steps, r_host["ms"])
+    peaks = measured_peaks()
+    pm, pf, pl = r_dev["prof"]
+    achieved = pf / (pm / 1e3) / 1e12 if pm > 0 else 0.0
+    line = {
+        "metric": "pages/sec end-to-end", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r_dev["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[4]: synthetic 1280x1280 pages end-to-end, 300 words/page, reference defaults "
+                               "(canvas 1024), CRAFT output overridden by the page's synthetic score map after CRAFT ran",
+                   "pages_per_gpu_per_step": n, "craft_batch_pages": args.batch_pages, "crops_per_page": WORDS,
+                   "weights": "seeded random init (CRAFT VGG16-BN, PARSeq-base)", "parallelism": f"dp{world} (pages)",
+                   "l2": f"inputs larger than L2: {n * PAGE * PAGE * 3 / 2**20:.0f} MiB of distinct pages per step"},
+        "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": r_host["h2d"], "d2h_bytes_per_step": r_host["d2h"],
+                "ms_per_step": r_host["ms"] / args.steps},
+        "gpu_launches": int(r_dev["launches"]),
+        "clocks": r_dev["clocks"],
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)",
+                     "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["source"],
+                     "launches": int(pl), "kernel_ms_per_step": pm / args.steps,
+                     "kernel_share_of_step": pm / r_dev["ms"],
+                     "algorithmic_gflop_per_step": n * (CRAFT_GFLOP_PER_PAGE + WORDS * PARSEQ_GFLOP_PER_CROP)},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sec, npg, threads = cpu_pipeline_sample(1)
+        line["cpu_baseline"] = {"value": npg / sec, "unit": "pages/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{npg} page (300 crops), oracle (torch CPU + cv2), torch threads {threads}, "
+                                          "PARSeq chunks of 4 on 6 threads (tuatara.cpp:452-475), models pre-loaded"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--pages-per-gpu", type=int, default=64)
+    ap.add_argument("--batch-pages", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_native(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,6 +90,15 @@ TT_API void tt_result_free(tt_result* r);
 /* Kernel launches issued by this library so far (bench.py's gpu_launches). */
 TT_API unsigned long long tt_launch_count(void);
 
+/* cudaStream_t the engine's idx-th device works on (bench.py records its CUDA events there). */
+TT_API void* tt_engine_stream(tt_engine* e, int idx);
+/* Host<->device bytes moved by tt_ocr_pages* so far (bench.py's h2d/d2h_bytes_per_step). */
+TT_API void tt_io_bytes(unsigned long long* h2d, unsigned long long* d2h);
+/* Per-launch CUDA-event timing of the tensor-core GEMM/conv kernel. tt_profile_collect waits for the
+ * recorded launches, returns their summed duration, algorithmic FLOPs and count, and clears the log. */
+TT_API void tt_profile_enable(int on);
+TT_API void tt_profile_collect(double* total_ms, double* total_flops, unsigned long long* launches);
+
 /* ---------------------------------------------------- stage level, host memory */
 /* Size arithmetic of resize_aspect_ratio (tuatara.cpp:211-226), fp32 like the reference. */
 TT_API int tt_resize_plan(int rows, int cols, float canvas_size, float mag_ratio, int* target_h, int* target_w, int* h32,

@@ -1,0 +1,127 @@
+"""Host-side logic of the product (geometry, size arithmetic, tokenizer) through the C ABI, bit-exact
+against cv2 / the oracle / the golden fixtures.  Runs without a GPU."""
+from pathlib import Path
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+import tuatara_b200 as tb
+from oracle import tuatara_ref as R
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def rect_bits(r):
+    return bits([r[0][0], r[0][1], r[1][0], r[1][1], r[2]])
+
+
+def test_min_area_rect_and_hull_random_pixel_sets(native_lib):
+    rng = np.random.default_rng(0)
+    for t in range(600):
+        h, w = rng.integers(3, 40), rng.integers(3, 60)
+        if t % 3 == 0:
+            yy, xx = np.mgrid[0:h, 0:w]
+            cx, cy = rng.uniform(0, w), rng.uniform(0, h)
+            m = ((xx - cx) ** 2 / rng.uniform(2, 200) + (yy - cy) ** 2 / rng.uniform(2, 80)
+                 + rng.uniform(-.5, .5) * (xx - cx) * (yy - cy) / 30) < 1
+        else:
+            m = rng.random((h, w)) < rng.uniform(0.05, 0.9)
+        pts = cv2.findNonZero(m.astype(np.uint8))
+        if pts is None:
+            continue
+        pts = pts.reshape(-1, 2)
+        assert np.array_equal(cv2.convexHull(pts, clockwise=False, returnPoints=False).reshape(-1), tb.convex_hull(pts))
+        assert np.array_equal(rect_bits(cv2.minAreaRect(pts)), rect_bits(tb.min_area_rect(pts)))
+
+
+def test_min_area_rect_degenerate(native_lib):
+    rng = np.random.default_rng(1)
+    for t in range(700):
+        k = t % 7
+        if k == 0:
+            pts = np.array([[rng.integers(0, 50), rng.integers(0, 50)]])
+        elif k == 1:
+            x = rng.integers(0, 50); pts = np.array([[x, y] for y in range(rng.integers(0, 20), rng.integers(20, 40))])
+        elif k == 2:
+            y = rng.integers(0, 50); pts = np.array([[x, y] for x in range(rng.integers(0, 20), rng.integers(20, 40))])
+        elif k == 3:
+            a = rng.integers(0, 30); pts = np.array([[a + i, a + i] for i in range(rng.integers(2, 20))])
+        elif k == 4:
+            a = rng.integers(0, 30); L = rng.integers(2, 20); pts = np.array([[a + L - i, a + i] for i in range(L)])
+        elif k == 5:
+            pts = rng.integers(0, 30, size=(2, 2))
+        else:
+            pts = np.unique(rng.integers(0, 12, size=(rng.integers(3, 7), 2)), axis=0)
+        pts = pts[np.lexsort((pts[:, 0], pts[:, 1]))].astype(np.int32)
+        assert np.array_equal(rect_bits(cv2.minAreaRect(pts)), rect_bits(tb.min_area_rect(pts))), pts.tolist()
+
+
+def test_rotated_rect_points_bounding_adjust_bbox(native_lib):
+    rng = np.random.default_rng(2)
+    for t in range(1500):
+        rect = ((float(np.float32(rng.uniform(0, 500))), float(np.float32(rng.uniform(0, 500)))),
+                (float(np.float32(rng.uniform(0.5, 200))), float(np.float32(rng.uniform(0.5, 100)))),
+                float(np.float32(rng.uniform(-90, 0))))
+        if t % 3 == 0:
+            rect = (rect[0], rect[1], -90.0)
+        if t % 11 == 0:
+            rect = ((float(rng.integers(0, 500)) + 0.5 * rng.integers(0, 2), float(rng.integers(0, 500))),
+                    (float(rng.integers(1, 100)), float(rng.integers(1, 100))), -90.0)
+        assert np.array_equal(bits(R.rect_points(rect)), bits(tb.rect_points(rect)))
+        assert R.rect_bounding(rect) == tb.rect_bounding(rect)
+        assert R.rotated_rect_to_tesseract_format(rect) == tb.rect_to_bbox(rect)
+        s = np.float32(np.float32(1) / np.float32(rng.choice([0.8, 1.0, 0.64, 0.9078014, 0.5])))
+        ref = R.adjust_result_coordinates([rect], s, s)[0]
+        assert np.array_equal(rect_bits(ref), rect_bits(tb.adjust_rect(rect, s, s, 2.0)))
+
+
+def test_golden_adjust_bbox_bounding(native_lib):
+    g = np.load(GOLD / "postprocess.npz")
+    inv = np.float32(1) / np.float32(0.8)
+    for name in ("synth", "blobs"):
+        for r, adj, bb, br in zip(g[name + "_rects"], g[name + "_adjusted"], g[name + "_bbox"], g[name + "_bounding"]):
+            rect = ((r[0], r[1]), (r[2], r[3]), r[4])
+            got = tb.adjust_rect(rect, inv, inv, 2.0)
+            assert np.array_equal(rect_bits(got), bits(adj))
+            assert tb.rect_to_bbox(got) == [float(v) for v in bb]
+            assert tb.rect_bounding(got) == tuple(int(v) for v in br)
+
+
+def test_resize_plan_matches_reference_float32_arithmetic(native_lib):
+    rng = np.random.default_rng(3)
+    sizes = [(1280, 1280), (763, 607), (1000, 754), (664, 1245), (206, 275), (1128, 300), (1134, 1134), (1171, 900)]
+    sizes += [(int(rng.integers(1, 6000)), int(rng.integers(1, 6000))) for _ in range(3000)]
+    n1023 = 0
+    for h, w in sizes:
+        th, tw, h32, w32, ratio = R.resize_target(h, w, 1024)
+        assert tb.resize_plan(h, w) == (th, tw, h32, w32, np.float32(ratio)), (h, w)
+        n1023 += max(th, tw) == 1023
+    assert n1023 > 0  # the float32 quirk is exercised
+
+
+def test_tokenizer_table_matches_compiled_kat_and_oracle(native_lib):
+    kat = (GOLD / "tokenizer_kat.txt").read_text().split()
+    n, eos, bos, pad = map(int, kat[:4])
+    itos_ref = bytes.fromhex(kat[4]).decode("latin-1")
+    itos, e, b, p = tb.tokenizer_table()
+    assert (len(itos), e, b, p) == (n, eos, bos, pad) == (98, 88, 96, 97)
+    assert itos == itos_ref
+    tok = R.Tokenizer()
+    assert tok.itos == itos and (tok.eos_id, tok.bos_id, tok.pad_id) == (88, 96, 97)
+    assert itos[0] == "]" and itos[69] == "\\" and itos[96] == "[" and itos[97] == "P"
+
+
+def test_decode_matches_reference_tokenizer(native_lib):
+    rng = np.random.default_rng(0)
+    tok = R.Tokenizer()
+    logits = torch.from_numpy(rng.standard_normal((300, 26, 95)).astype(np.float32))
+    logits[:50, 3, 0] = 50.0    # class 0 -> ']' terminates
+    logits[50:100, 2, 88] = 50.0  # class 88 is silently dropped
+    ref = [R.truncate_at_eos(t) for t in tok.decode(torch.softmax(logits, -1))]
+    assert tb.decode_ids(logits.argmax(-1).numpy().astype(np.int32)) == ref

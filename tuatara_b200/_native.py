@@ -61,6 +61,10 @@ SIGNATURES = {
     "tt_ocr_pages_ex": (_I, [_P, C.POINTER(tt_image), _I, C.POINTER(tt_ocr_options), C.POINTER(C.POINTER(tt_result))]),
     "tt_result_free": (None, [C.POINTER(tt_result)]),
     "tt_launch_count": (C.c_ulonglong, []),
+    "tt_engine_stream": (_P, [_P, _I]),
+    "tt_io_bytes": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
+    "tt_profile_enable": (None, [_I]),
+    "tt_profile_collect": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "tt_resize_plan": (_I, [_I, _I, _F, _F, _PI, _PI, _PI, _PI, _PF]),
     "tt_preprocess": (_I, [C.POINTER(tt_image), _F, _F, _P]),
     "tt_craft_forward": (_I, [_P, _P, _I, _I, _P]),

@@ -3,6 +3,7 @@
 #include <map>
 #include <mutex>
 #include <utility>
+#include <vector>
 
 namespace tt {
 
@@ -11,6 +12,47 @@ std::atomic<unsigned long long> g_launches{0};
 
 void set_error(const std::string& msg) { t_last_error = msg; }
 const char* last_error() { return t_last_error.c_str(); }
+
+std::atomic<unsigned long long> g_h2d_bytes{0}, g_d2h_bytes{0};
+
+namespace {
+struct ProfRec { cudaEvent_t a, b; double flops, bytes; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+std::atomic<bool> g_prof_on{false};
+thread_local cudaEvent_t t_open = nullptr;
+}  // namespace
+
+void prof_enable(bool on) { g_prof_on.store(on); }
+bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+
+void prof_record(cudaStream_t s, bool begin, double flops, double bytes) {
+  if (!prof_enabled()) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, s);
+  if (begin) { t_open = ev; return; }
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof.push_back(ProfRec{t_open, ev, flops, bytes});
+  t_open = nullptr;
+}
+
+void prof_collect(double* total_ms, double* total_flops, double* total_bytes, unsigned long long* launches) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  double ms = 0, fl = 0, by = 0;
+  for (ProfRec& r : g_prof) {
+    cudaEventSynchronize(r.b);
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms += t; fl += r.flops; by += r.bytes; }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (total_bytes) *total_bytes = by;
+  if (launches) *launches = g_prof.size();
+  g_prof.clear();
+}
 
 cudaError_t ensure_dynamic_smem(const void* func, int bytes) {
   static std::mutex mu;

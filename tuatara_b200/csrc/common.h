@@ -13,6 +13,13 @@ void set_error(const std::string& msg);
 const char* last_error();
 extern std::atomic<unsigned long long> g_launches;
 inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern std::atomic<unsigned long long> g_h2d_bytes, g_d2h_bytes;  // engine-level host<->device traffic
+// Optional per-launch CUDA-event timing of the tensor-core kernel (bench.py's roofline): when on,
+// every gemm_tc launch is bracketed by two events on its stream; prof_collect() resolves them.
+void prof_enable(bool on);
+bool prof_enabled();
+void prof_record(cudaStream_t s, bool begin, double flops, double bytes);  // begin/end pair around a launch
+void prof_collect(double* total_ms, double* total_flops, double* total_bytes, unsigned long long* launches);
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: set it once per (kernel, device).
 cudaError_t ensure_dynamic_smem(const void* func, int bytes);
 

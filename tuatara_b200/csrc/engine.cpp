@@ -65,6 +65,7 @@ int detect_boxes(DeviceCtx& d, const tt_config& cfg, const float* maps_dev, int 
     E_TRY(d.ensure_pinned(bytes));
     E_CUDA(cudaMemcpyAsync(d.pinned, ws.result, bytes, cudaMemcpyDeviceToHost, d.stream));
     E_CUDA(cudaStreamSynchronize(d.stream));
+    g_d2h_bytes += bytes;
     out->assign(batch, {});
     bool ok = true;
     for (int b = 0; b < batch && ok; ++b)
@@ -104,6 +105,7 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
     } else {
       E_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(im.cols) * 3, im.data, im.step,
                                static_cast<size_t>(im.cols) * 3, im.rows, page_kind, d.stream));
+      g_h2d_bytes += page_bytes;
       refs[b] = PageRef{dst, im.rows, im.cols, static_cast<size_t>(im.cols) * 3};
     }
     E_TRY(page_resize_pad(refs[b].data, im.rows, im.cols, refs[b].step, craft_in + b * in_bytes, th, tw, h32, w32,
@@ -115,8 +117,11 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
     const size_t map_elems = static_cast<size_t>(h32 / 2) * (w32 / 2) * 2;
     for (int b = 0; b < B; ++b)
       if (opt.score_override[idx[b]])
+      {
         E_CUDA(cudaMemcpyAsync(maps + b * map_elems, opt.score_override[idx[b]], map_elems * sizeof(float),
                                opt.override_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d.stream));
+        if (!opt.override_on_device) g_h2d_bytes += map_elems * sizeof(float);
+      }
   }
   std::vector<std::vector<DetBox>> det;
   if (detect_boxes(d, cfg, maps, B, h32 / 2, w32 / 2, &det)) return 1;
@@ -175,6 +180,8 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
     if (!refs_dev || !boxes_dev || !patches) { set_error("arena exhausted (crops)"); return 1; }
     E_CUDA(cudaMemcpyAsync(refs_dev, refs.data(), sizeof(PageRef) * B, cudaMemcpyHostToDevice, d.stream));
     E_CUDA(cudaMemcpyAsync(boxes_dev, crops.data() + c0, sizeof(CropBox) * nc, cudaMemcpyHostToDevice, d.stream));
+    g_h2d_bytes += sizeof(PageRef) * B + sizeof(CropBox) * nc + sizeof(int) * nc * d.pd.L /*token init*/;
+    g_d2h_bytes += sizeof(int) * nc * d.pd.L;
     E_TRY(crop_resize(refs_dev, boxes_dev, nc, nullptr, patches, d.stream));
     float* logits = nullptr;
     int* ids = nullptr;
@@ -248,6 +255,19 @@ int tt_engine_create(const char* weights_dir, const int* devices, int n_devices,
 }
 
 void tt_engine_destroy(tt_engine* e) { delete e; }
+
+void* tt_engine_stream(tt_engine* e, int idx) {
+  if (!e || idx < 0 || idx >= static_cast<int>(e->devs.size())) return nullptr;
+  return e->devs[idx]->stream;
+}
+void tt_io_bytes(unsigned long long* h2d, unsigned long long* d2h) {
+  if (h2d) *h2d = g_h2d_bytes.load();
+  if (d2h) *d2h = g_d2h_bytes.load();
+}
+void tt_profile_enable(int on) { prof_enable(on != 0); }
+void tt_profile_collect(double* total_ms, double* total_flops, unsigned long long* launches) {
+  prof_collect(total_ms, total_flops, nullptr, launches);
+}
 
 int tt_ocr_pages(tt_engine* e, const tt_image* pages, int n_pages, tt_result** out) {
   return tt_ocr_pages_ex(e, pages, n_pages, nullptr, out);

@@ -394,7 +394,7 @@ int pick_bn(int N, long long m_tiles) {
   return best;
 }
 
-cudaError_t launch(KParams& kp, cudaStream_t s) {
+cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   const int row_bytes = kp.BK * 2;
   const int stage_bytes = kBlockM * row_bytes + kp.BN * row_bytes;
   kp.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - 1024) / stage_bytes));
@@ -402,7 +402,9 @@ cudaError_t launch(KParams& kp, cudaStream_t s) {
   TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_tc_kernel), 227 * 1024));
   const int total = kp.num_m_tiles * kp.num_n_tiles;
   const int grid = std::min(total, num_sms());
+  prof_record(s, true, 0, 0);
   gemm_tc_kernel<<<grid, kThreads, smem, s>>>(kp);
+  prof_record(s, false, flops, 0);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -467,7 +469,8 @@ cudaError_t conv_forward(const ConvProblem& c, const Epilogue& e, cudaStream_t s
     const cuuint32_t box[2] = {static_cast<cuuint32_t>(kp.BK), static_cast<cuuint32_t>(kp.BN)};
     if (!make_map(&kp.tmB, c.weight, 2, dims, strides, box, row_bytes)) return cudaErrorInvalidValue;
   }
-  return launch(kp, s);
+  const double k_algo = c.algo_k > 0 ? c.algo_k : static_cast<double>(c.taps) * ctot;
+  return launch(kp, s, 2.0 * c.batch * c.H * c.W * c.Cout * k_algo);
 }
 
 cudaError_t linear_forward(const LinearProblem& l, const Epilogue& e, cudaStream_t s) {
@@ -501,7 +504,7 @@ cudaError_t linear_forward(const LinearProblem& l, const Epilogue& e, cudaStream
     const cuuint32_t box[2] = {static_cast<cuuint32_t>(kp.BK), static_cast<cuuint32_t>(kp.BN)};
     if (!make_map(&kp.tmB, l.W, 2, dims, strides, box, row_bytes)) return cudaErrorInvalidValue;
   }
-  return launch(kp, s);
+  return launch(kp, s, 2.0 * l.M * (l.algo_n > 0 ? l.algo_n : l.N) * l.K);
 }
 
 }  // namespace tt

@@ -46,6 +46,7 @@ struct ConvProblem {
   const __nv_bfloat16* weight = nullptr;  // [Cout][taps][C0 + C1], K-major
   int Cout = 0;
   int BN = 0;                     // 0 = choose
+  int algo_k = 0;                 // true K for FLOP accounting when the stored K is padded (conv1_1: 27)
 };
 
 struct LinearProblem {
@@ -55,6 +56,7 @@ struct LinearProblem {
   const __nv_bfloat16* W = nullptr;  // [N][K]
   int N = 0;
   int BN = 0;
+  int algo_n = 0;                    // true N for FLOP accounting when N is padded (head: 95)
 };
 
 // Both return cudaSuccess or the first error (also recorded via tt::set_error).
@@ -66,7 +68,5 @@ cudaError_t linear_forward(const LinearProblem& p, const Epilogue& e, cudaStream
 bool make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                     const cuuint32_t* box, int row_bytes);
 
-// Number of kernel launches issued through the two entry points above (bench bookkeeping).
-uint64_t gemm_launch_count();
 
 }  // namespace tt

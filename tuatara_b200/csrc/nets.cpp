@@ -117,6 +117,7 @@ cudaError_t DeviceCtx::craft_forward(const uint8_t* in, int B, int H, int W, flo
     c.nsrc = 1;
     if (b) { c.src[1] = ConvSrc{b, Cb, Cb}; c.nsrc = 2; }
     c.taps = taps; c.dil = dil; c.Cout = cout;
+    if (Ca == 32 && taps == 1 && cout == 64) c.algo_k = 27;  // conv1_1: 3x3x3 taps stored padded to 32
     c.weight = craft.bf(std::string(name) + ".w");
     Epilogue e;
     e.bias = craft.f32(std::string(name) + ".b");
@@ -228,6 +229,7 @@ static cudaError_t lin(cudaStream_t s, const __nv_bfloat16* A, int lda, int M, i
                        int out_type, int ldc) {
   LinearProblem l;
   l.A = A; l.lda = lda; l.M = M; l.K = K; l.W = W; l.N = N;
+  if (N == 96) l.algo_n = 95;  // head: 95 classes stored padded to 96
   Epilogue e;
   e.bias = bias; e.act = act; e.residual = res; e.res_type = res_type; e.ldr = ldr; e.res_mod = res_mod;
   e.out = out; e.out_type = out_type; e.ldc = ldc;

@@ -162,3 +162,83 @@ def export_parseq(state_dict: dict, path: str | Path) -> None:
                                 sd["pos_queries"].shape[1], sd["text_embed.embedding.weight"].shape[0]],
                                dtype=torch.int32)
     write_ttw(path, out)
+
+
+# ------------------------------------------------------------- seeded random-init checkpoints
+def random_craft_state_dict(seed: int = 0) -> dict:
+    """A CRAFT ``state_dict`` (upstream names/shapes) with He-initialised convs and randomised
+    BatchNorm statistics -- stands in for the HuggingFace checkpoint (setup.sh:6) offline."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(key, cout, cin, k):
+        sd[key + ".weight"] = torch.randn(cout, cin, k, k, generator=g) * math.sqrt(2.0 / (cin * k * k))
+        sd[key + ".bias"] = torch.randn(cout, generator=g) * 0.05
+
+    def bn(key, c):
+        sd[key + ".weight"] = 1.0 + 0.2 * (torch.rand(c, generator=g) - 0.5)
+        sd[key + ".bias"] = 0.1 * torch.randn(c, generator=g)
+        sd[key + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
+        sd[key + ".running_var"] = 0.75 + 0.5 * torch.rand(c, generator=g)
+
+    chans = {"c1_1": (3, 64), "c1_2": (64, 64), "c2_1": (64, 128), "c2_2": (128, 128), "c3_1": (128, 256),
+             "c3_2": (256, 256), "c3_3": (256, 256), "c4_1": (256, 512), "c4_2": (512, 512), "c4_3": (512, 512),
+             "c5_1": (512, 512), "c5_2": (512, 512), "fc6": (512, 1024), "fc7": (1024, 1024),
+             "up1a": (1536, 512), "up1b": (512, 256), "up2a": (768, 256), "up2b": (256, 128),
+             "up3a": (384, 128), "up3b": (128, 64), "up4a": (192, 64), "up4b": (64, 32),
+             "cls1": (32, 32), "cls2": (32, 32), "cls3": (32, 16)}
+    one_by_one = {"fc7", "up1a", "up2a", "up3a", "up4a"}
+    for name, ck, bk in CRAFT_LAYERS:
+        cin, cout = chans[name]
+        conv(ck, cout, cin, 1 if name in one_by_one else 3)
+        if bk is not None:
+            bn(bk, cout)
+    conv("conv_cls.6", 16, 16, 1)
+    conv("conv_cls.8", 2, 16, 1)
+    return sd
+
+
+def random_parseq_state_dict(seed: int = 0, d: int = 384, depth: int = 12, mlp: int = 1536, n_tok: int = 97,
+                             max_len: int = 25) -> dict:
+    """A PARSeq ``state_dict`` (upstream names/shapes), scaled so attention is not uniform."""
+    g = torch.Generator().manual_seed(seed + 1000)
+    rn = lambda shape, std: torch.randn(shape, generator=g) * std  # noqa: E731
+    sd = {}
+
+    def linear(key, out, inp, std=0.05):
+        sd[key + ".weight"], sd[key + ".bias"] = rn((out, inp), std), rn((out,), 0.02)
+
+    def norm(key):
+        sd[key + ".weight"], sd[key + ".bias"] = 1.0 + 0.2 * (torch.rand(d, generator=g) - 0.5), rn((d,), 0.05)
+
+    sd["encoder.patch_embed.proj.weight"], sd["encoder.patch_embed.proj.bias"] = rn((d, 3, 4, 8), 0.1), rn((d,), 0.02)
+    sd["encoder.pos_embed"] = rn((1, 128, d), 0.2)
+    for i in range(depth):
+        p = f"encoder.blocks.{i}."
+        norm(p + "norm1"); norm(p + "norm2")
+        linear(p + "attn.qkv", 3 * d, d); linear(p + "attn.proj", d, d)
+        linear(p + "mlp.fc1", mlp, d); linear(p + "mlp.fc2", d, mlp)
+    norm("encoder.norm")
+    L = "decoder.layers.0."
+    for a in ("self_attn", "cross_attn"):
+        sd[L + a + ".in_proj_weight"], sd[L + a + ".in_proj_bias"] = rn((3 * d, d), 0.05), rn((3 * d,), 0.02)
+        linear(L + a + ".out_proj", d, d)
+    linear(L + "linear1", mlp, d); linear(L + "linear2", d, mlp)
+    for k in ("norm1", "norm2", "norm_q", "norm_c"):
+        norm(L + k)
+    norm("decoder.norm")
+    linear("head", n_tok - 2, d, 0.2)
+    sd["text_embed.embedding.weight"] = rn((n_tok, d), 0.05)
+    sd["pos_queries"] = rn((1, max_len + 1, d), 0.5)
+    return sd
+
+
+def export_random(out_dir: str | Path, seed: int = 0) -> str:
+    """craft.ttw + parseq.ttw with seeded random-init weights of the named architectures."""
+    out_dir = Path(out_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    if not (out_dir / "craft.ttw").exists():
+        export_craft(random_craft_state_dict(seed), out_dir / "craft.ttw")
+    if not (out_dir / "parseq.ttw").exists():
+        export_parseq(random_parseq_state_dict(seed), out_dir / "parseq.ttw")
+    return str(out_dir)
