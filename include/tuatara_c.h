@@ -98,6 +98,8 @@ TT_API void tt_io_bytes(unsigned long long* h2d, unsigned long long* d2h);
  * recorded launches, returns their summed duration, algorithmic FLOPs and count, and clears the log. */
 TT_API void tt_profile_enable(int on);
 TT_API void tt_profile_collect(double* total_ms, double* total_flops, unsigned long long* launches);
+/* Same, and appends one CSV line per launch ("tag,flops,ms") to `path` (per-layer tables in profiles/). */
+TT_API void tt_profile_dump(const char* path, double* total_ms, double* total_flops, unsigned long long* launches);
 
 /* ---------------------------------------------------- stage level, host memory */
 /* Size arithmetic of resize_aspect_ratio (tuatara.cpp:211-226), fp32 like the reference. */
@@ -139,13 +141,16 @@ TT_API int tt_rect_to_bbox(const float rect[5], float bbox_out[4]);
 
 /* --------------------------------------- stage level, device memory (bench / kernel tests) */
 /* out[M][N] = act(A[M][K] * W[N][K]^T + bias) (+ residual). All pointers are device pointers;
- * A, W bf16; bias fp32; out bf16 (out_f32 == 0) or fp32. act: 0 none, 1 relu, 2 gelu. */
+ * A, W bf16; bias fp32; out bf16 (out_f32 == 0) or fp32. act: 0 none, 1 relu, 2 gelu.
+ * BN: N tile (0 = planner decides); resident: with BN given, 1 = weight-resident schedule. */
 TT_API int tt_linear_dev(const void* A, int lda, int M, int K, const void* W, int N, const float* bias, int act,
-                  const void* residual, int res_f32, int ldr, void* out, int out_f32, int ldc, int BN, void* stream);
+                  const void* residual, int res_f32, int ldr, void* out, int out_f32, int ldc, int BN, int resident,
+                  void* stream);
 /* NHWC bf16 stride-1 "same" convolution as implicit GEMM; src1 may be NULL (else channel concat).
  * weight bf16 [Cout][taps][C0+C1]; out bf16 [batch][H][W][Cout]. */
 TT_API int tt_conv_dev(const void* src0, int C0, const void* src1, int C1, int batch, int H, int W, int taps, int dil,
-                const void* weight, const float* bias, int Cout, int relu, void* out, int BN, void* stream);
+                const void* weight, const float* bias, int Cout, int relu, void* out, int BN, int resident,
+                void* stream);
 /* Batched device-side post-processing (bench): maps_dev [batch][H][W][2] fp32. Returns total rects. */
 TT_API int tt_postprocess_dev(tt_engine* e, const float* maps_dev, int batch, int H, int W, int* n_rects_total,
                        void* stream);

@@ -9,7 +9,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _lin(native_lib, M, K, N, act=0, bias=True, res=None, out_f32=False, BN=0, seed=0):
+def _lin(native_lib, M, K, N, act=0, bias=True, res=None, out_f32=False, BN=0, seed=0, resident=0):
     from tuatara_b200._native import check
 
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -24,7 +24,7 @@ def _lin(native_lib, M, K, N, act=0, bias=True, res=None, out_f32=False, BN=0, s
     out = torch.full((M, N), float("nan"), dtype=torch.float32 if out_f32 else torch.bfloat16, device="cuda")
     check(native_lib.tt_linear_dev(A.data_ptr(), K, M, K, W.data_ptr(), N, b.data_ptr() if bias else None, act,
                                    R.data_ptr() if R is not None else None, int(res == "f32"), N,
-                                   out.data_ptr(), int(out_f32), N, BN, None), "tt_linear_dev")
+                                   out.data_ptr(), int(out_f32), N, BN, resident, None), "tt_linear_dev")
     torch.cuda.synchronize()
     ref = A.float() @ W.float().t()
     if bias:
@@ -61,6 +61,28 @@ def test_linear_shapes(native_lib, M, K, N, BN):
     _check(out, ref, K, f"linear M{M} K{K} N{N} BN{BN}")
 
 
+@pytest.mark.parametrize("M,K,N,BN", [(5000, 384, 1152, 192), (131072, 384, 384, 192), (3000, 96, 384, 192),
+                                      (70000, 384, 1536, 192), (2000, 64, 64, 64), (1200, 384, 768, 128)])
+def test_linear_weight_resident(native_lib, M, K, N, BN):
+    """The weight-resident schedule (B slice loaded once per CTA, only A streams)."""
+    out, ref = _lin(native_lib, M, K, N, BN=BN, act=2 if N == 1536 else 0, res="f32" if N == 384 else None,
+                    out_f32=(N == 384), resident=1)
+    _check(out, ref, K, f"resident linear M{M} K{K} N{N} BN{BN}")
+
+
+def test_linear_auto_plan_large(native_lib):
+    for (M, K, N) in [(131072, 384, 1152), (131072, 1536, 384), (2400, 384, 384), (26 * 300, 384, 96)]:
+        out, ref = _lin(native_lib, M, K, N)
+        _check(out, ref, K, f"auto linear M{M} K{K} N{N}")
+
+
+def test_conv_weight_resident(native_lib):
+    for (B, H, W, C0, C1, Cout, taps, BN) in [(2, 64, 64, 64, 0, 64, 9, 64), (1, 128, 96, 128, 256, 128, 1, 128),
+                                              (1, 96, 128, 32, 0, 32, 9, 32)]:
+        out, ref = _conv(native_lib, B, H, W, C0, C1, Cout, taps, 1, BN=BN, resident=1)
+        _check(out.reshape(-1, Cout), ref.reshape(-1, Cout), taps * (C0 + C1), f"resident conv {H}x{W} C{C0}+{C1}->{Cout}")
+
+
 @pytest.mark.parametrize("act,res,out_f32", [(1, None, False), (2, None, False), (0, "bf16", False),
                                              (0, "f32", True), (0, None, True)])
 def test_linear_epilogues(native_lib, act, res, out_f32):
@@ -68,7 +90,7 @@ def test_linear_epilogues(native_lib, act, res, out_f32):
     _check(out, ref, 384, f"linear act{act} res{res} f32{out_f32}")
 
 
-def _conv(native_lib, B, H, W, C0, C1, Cout, taps, dil, relu=1, BN=0, seed=0):
+def _conv(native_lib, B, H, W, C0, C1, Cout, taps, dil, relu=1, BN=0, seed=0, resident=0):
     from tuatara_b200._native import check
 
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -80,7 +102,7 @@ def _conv(native_lib, B, H, W, C0, C1, Cout, taps, dil, relu=1, BN=0, seed=0):
     b = torch.randn(Cout, generator=g).float().cuda()
     out = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
     check(native_lib.tt_conv_dev(x0.data_ptr(), C0, x1.data_ptr() if C1 else None, C1, B, H, W, taps, dil,
-                                 w.data_ptr(), b.data_ptr(), Cout, relu, out.data_ptr(), BN, None), "tt_conv_dev")
+                                 w.data_ptr(), b.data_ptr(), Cout, relu, out.data_ptr(), BN, resident, None), "tt_conv_dev")
     torch.cuda.synchronize()
     xin = x0.float() if not C1 else torch.cat([x0.float(), x1.float()], -1)
     ref = torch.nn.functional.conv2d(xin.permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b,

@@ -65,6 +65,7 @@ SIGNATURES = {
     "tt_io_bytes": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "tt_profile_enable": (None, [_I]),
     "tt_profile_collect": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
+    "tt_profile_dump": (None, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "tt_resize_plan": (_I, [_I, _I, _F, _F, _PI, _PI, _PI, _PI, _PF]),
     "tt_preprocess": (_I, [C.POINTER(tt_image), _F, _F, _P]),
     "tt_craft_forward": (_I, [_P, _P, _I, _I, _P]),
@@ -81,8 +82,8 @@ SIGNATURES = {
     "tt_rect_bounding": (_I, [_P, _P]),
     "tt_adjust_rect": (_I, [_P, _F, _F, _F, _P]),
     "tt_rect_to_bbox": (_I, [_P, _P]),
-    "tt_linear_dev": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _P, _I, _I, _I, _P]),
-    "tt_conv_dev": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P]),
+    "tt_linear_dev": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P]),
+    "tt_conv_dev": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P]),
     "tt_postprocess_dev": (_I, [_P, _P, _I, _I, _I, _PI, _P]),
 }
 

@@ -252,11 +252,12 @@ int tt_rect_to_bbox(const float rect[5], float bbox_out[4]) {
 }
 
 int tt_linear_dev(const void* A, int lda, int M, int K, const void* W, int N, const float* bias, int act,
-                  const void* residual, int res_f32, int ldr, void* out, int out_f32, int ldc, int BN, void* stream) {
+                  const void* residual, int res_f32, int ldr, void* out, int out_f32, int ldc, int BN, int resident,
+                  void* stream) {
   return guarded([&]() -> int {
     LinearProblem l;
     l.A = static_cast<const __nv_bfloat16*>(A); l.lda = lda; l.M = M; l.K = K;
-    l.W = static_cast<const __nv_bfloat16*>(W); l.N = N; l.BN = BN;
+    l.W = static_cast<const __nv_bfloat16*>(W); l.N = N; l.BN = BN; l.resident = BN ? resident : -1;
     Epilogue e;
     e.bias = bias; e.act = act;
     e.residual = residual; e.res_type = residual ? (res_f32 ? RES_F32 : RES_BF16) : RES_NONE; e.ldr = ldr;
@@ -266,7 +267,8 @@ int tt_linear_dev(const void* A, int lda, int M, int K, const void* W, int N, co
 }
 
 int tt_conv_dev(const void* src0, int C0, const void* src1, int C1, int batch, int H, int W, int taps, int dil,
-                const void* weight, const float* bias, int Cout, int relu, void* out, int BN, void* stream) {
+                const void* weight, const float* bias, int Cout, int relu, void* out, int BN, int resident,
+                void* stream) {
   return guarded([&]() -> int {
     ConvProblem c;
     c.batch = batch; c.H = H; c.W = W;
@@ -274,7 +276,7 @@ int tt_conv_dev(const void* src0, int C0, const void* src1, int C1, int batch, i
     c.nsrc = 1;
     if (src1) { c.src[1] = ConvSrc{static_cast<const __nv_bfloat16*>(src1), C1, C1}; c.nsrc = 2; }
     c.taps = taps; c.dil = dil;
-    c.weight = static_cast<const __nv_bfloat16*>(weight); c.Cout = Cout; c.BN = BN;
+    c.weight = static_cast<const __nv_bfloat16*>(weight); c.Cout = Cout; c.BN = BN; c.resident = BN ? resident : -1;
     Epilogue e;
     e.bias = bias; e.act = relu ? ACT_RELU : ACT_NONE; e.out = out; e.out_type = OUT_BF16; e.ldc = Cout;
     return conv_forward(c, e, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : 1;

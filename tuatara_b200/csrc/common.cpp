@@ -16,7 +16,7 @@ const char* last_error() { return t_last_error.c_str(); }
 std::atomic<unsigned long long> g_h2d_bytes{0}, g_d2h_bytes{0};
 
 namespace {
-struct ProfRec { cudaEvent_t a, b; double flops, bytes; };
+struct ProfRec { cudaEvent_t a, b; double flops, bytes; std::string tag; };
 std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
 std::atomic<bool> g_prof_on{false};
@@ -26,30 +26,34 @@ thread_local cudaEvent_t t_open = nullptr;
 void prof_enable(bool on) { g_prof_on.store(on); }
 bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
 
-void prof_record(cudaStream_t s, bool begin, double flops, double bytes) {
+void prof_record(cudaStream_t s, bool begin, double flops, double bytes, const char* tag) {
   if (!prof_enabled()) return;
   cudaEvent_t ev;
   if (cudaEventCreate(&ev) != cudaSuccess) return;
   cudaEventRecord(ev, s);
   if (begin) { t_open = ev; return; }
   std::lock_guard<std::mutex> lock(g_prof_mu);
-  g_prof.push_back(ProfRec{t_open, ev, flops, bytes});
+  g_prof.push_back(ProfRec{t_open, ev, flops, bytes, tag ? tag : ""});
   t_open = nullptr;
 }
 
-void prof_collect(double* total_ms, double* total_flops, double* total_bytes, unsigned long long* launches) {
+void prof_collect(double* total_ms, double* total_flops, double* total_bytes, unsigned long long* launches,
+                  const char* dump_path) {
   std::lock_guard<std::mutex> lock(g_prof_mu);
   double ms = 0, fl = 0, by = 0;
+  FILE* f = dump_path ? std::fopen(dump_path, "a") : nullptr;
   for (ProfRec& r : g_prof) {
     cudaEventSynchronize(r.b);
     float t = 0.f;
     if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms += t; fl += r.flops; by += r.bytes; }
+    if (f) std::fprintf(f, "%s,%.0f,%.6f\n", r.tag.c_str(), r.flops, t);
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;
   if (total_bytes) *total_bytes = by;
+  if (f) std::fclose(f);
   if (launches) *launches = g_prof.size();
   g_prof.clear();
 }

@@ -18,8 +18,10 @@ extern std::atomic<unsigned long long> g_h2d_bytes, g_d2h_bytes;  // engine-leve
 // every gemm_tc launch is bracketed by two events on its stream; prof_collect() resolves them.
 void prof_enable(bool on);
 bool prof_enabled();
-void prof_record(cudaStream_t s, bool begin, double flops, double bytes);  // begin/end pair around a launch
-void prof_collect(double* total_ms, double* total_flops, double* total_bytes, unsigned long long* launches);
+void prof_record(cudaStream_t s, bool begin, double flops, double bytes, const char* tag = nullptr);
+// dump_path != nullptr: also append one CSV line per launch (tag, flops, ms) to that file.
+void prof_collect(double* total_ms, double* total_flops, double* total_bytes, unsigned long long* launches,
+                  const char* dump_path = nullptr);
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: set it once per (kernel, device).
 cudaError_t ensure_dynamic_smem(const void* func, int bytes);
 

@@ -268,6 +268,9 @@ void tt_profile_enable(int on) { prof_enable(on != 0); }
 void tt_profile_collect(double* total_ms, double* total_flops, unsigned long long* launches) {
   prof_collect(total_ms, total_flops, nullptr, launches);
 }
+void tt_profile_dump(const char* path, double* total_ms, double* total_flops, unsigned long long* launches) {
+  prof_collect(total_ms, total_flops, nullptr, launches, path);
+}
 
 int tt_ocr_pages(tt_engine* e, const tt_image* pages, int n_pages, tt_result** out) {
   return tt_ocr_pages_ex(e, pages, n_pages, nullptr, out);

@@ -18,6 +18,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <mutex>
 
 #include "common.h"
@@ -33,7 +34,8 @@ constexpr int kEpiWarps = 8;
 constexpr int kMaxStages = 8;
 constexpr int kAccStride = 256;     // TMEM columns per accumulator stage
 constexpr int kTmemCols = 512;
-constexpr int kSmemBudget = 220 * 1024;
+constexpr int kSmemBudget = 222 * 1024;
+constexpr int kResidentMax = 144 * 1024;  // largest weight slice kept in smem (BN=192 x K=384 bf16)
 
 struct KParams {
   CUtensorMap tmA[2];
@@ -45,6 +47,7 @@ struct KParams {
   int H, W, TH, TW, tiles_x, tiles_y;
   int num_m_tiles, num_n_tiles;
   int stages;
+  int b_resident;  // 1: the CTA's [BN x K] weight slice is loaded once and stays in smem; only A streams
   Epilogue epi;
 };
 
@@ -53,27 +56,58 @@ struct SmemCtl {
   uint64_t empty[kMaxStages];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
+  uint64_t b_full;
   uint32_t tmem_base;
   float tail[16 * 16 + 16 + 2 * 16 + 2];
 };
 
-__device__ __forceinline__ float gelu_erf(float x) {
-  // 0.5 x (1 + erf(x / sqrt 2)); erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7), one ex2 + one rcp.
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float erf_abs = 1.0f - poly * __expf(-z * z);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+// Tile schedule shared by the three warp roles.  Streaming mode: tiles round-robin over CTAs with the
+// N index fastest (neighbouring CTAs share the A tile in L2).  Weight-resident mode: a CTA owns one
+// N slice for its whole life and walks M tiles with stride `groups`.
+struct TileIter {
+  int m, n, step, limit;
+  bool resident;
+  __device__ TileIter(const KParams& p) {
+    resident = p.b_resident != 0;
+    if (resident) {
+      const int groups = gridDim.x / p.num_n_tiles;
+      n = blockIdx.x % p.num_n_tiles;
+      m = blockIdx.x / p.num_n_tiles;
+      step = groups;
+      limit = p.num_m_tiles;
+    } else {
+      m = blockIdx.x;  // linear tile index in this mode
+      n = 0;
+      step = gridDim.x;
+      limit = p.num_m_tiles * p.num_n_tiles;
+    }
+  }
+  __device__ bool valid() const { return m < limit; }
+  __device__ void next() { m += step; }
+  __device__ int m_tile(const KParams& p) const { return resident ? m : m / p.num_n_tiles; }
+  __device__ int n_tile(const KParams& p) const { return resident ? n : m % p.num_n_tiles; }
+};
+
+// GELU(x) = x * Phi(x) evaluated as 0.5 x (1 + tanh(x (a + b x^2 + c x^4))) with (a, b, c) fitted to
+// the erf form: |error| <= 2.6e-5 on the real line (the textbook tanh form is off by 4.7e-4), plus
+// tanh.approx.f32's 2^-11 relative error -- both far below the bf16 rounding applied to the result.
+// 8 issue slots + 1 MUFU per element: the exact erf costs > 20 and made fc1's epilogue the bottleneck.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float x2 = fminf(x * x, 36.0f);  // tanh is saturated beyond |x| = 6; keeps the quartic monotone
+  float p = fmaf(x2, -0.00035151678866f, 0.037005646023f);
+  p = fmaf(x2, p, 0.797507884285f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+
+struct ResRegs { uint4 u[4]; };  // 16 fp32 or 16 bf16 (first two) residual values of one chunk
 
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -82,14 +116,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int row_bytes = p.BK * 2;
   const int a_bytes = kBlockM * row_bytes;
   const int b_bytes = p.BN * row_bytes;
-  const int stage_bytes = a_bytes + b_bytes;
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.stages * stage_bytes);
+  const int kb_per_tap = p.kb_src[0] + p.kb_src[1];
+  const int num_kb = p.taps * kb_per_tap;
+  const bool resident = p.b_resident != 0;
+  const int stage_bytes = resident ? a_bytes : a_bytes + b_bytes;
+  uint8_t* sBres = smem;                                        // [num_kb][BN rows] when resident
+  uint8_t* ring = smem + (resident ? num_kb * b_bytes : 0);
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(ring + p.stages * stage_bytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int kb_per_tap = p.kb_src[0] + p.kb_src[1];
-  const int num_kb = p.taps * kb_per_tap;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&p.tmA[0]);
@@ -103,6 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       ptx::mbar_init(&ctl->acc_full[s], 1);
       ptx::mbar_init(&ctl->acc_empty[s], kEpiWarps);
     }
+    ptx::mbar_init(&ctl->b_full, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(&ctl->tmem_base, kTmemCols);
@@ -117,11 +154,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
+      TileIter it(p);
+      if (resident && it.valid()) {
+        ptx::mbar_arrive_expect_tx(&ctl->b_full, static_cast<uint32_t>(num_kb * b_bytes));
+        for (int kb = 0; kb < num_kb; ++kb)
+          ptx::tma_load_2d(sBres + kb * b_bytes, &p.tmB, &ctl->b_full, kb * p.BK, it.n_tile(p) * p.BN);
+      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.num_n_tiles;
-        const int m_tile = tile / p.num_n_tiles;
+      for (; it.valid(); it.next()) {
+        const int n_tile = it.n_tile(p), m_tile = it.m_tile(p);
         int img = 0, y0 = 0, x0 = 0;
         if (p.mode == 1) {
           const int per_img = p.tiles_x * p.tiles_y;
@@ -130,21 +172,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           y0 = (t / p.tiles_x) * p.TH;
           x0 = (t % p.tiles_x) * p.TW;
         }
+        int kb = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = (p.taps == 9) ? (tap / 3 - 1) * p.dil : 0;
           const int dx = (p.taps == 9) ? (tap % 3 - 1) * p.dil : 0;
           for (int src = 0; src < 2; ++src) {
-            for (int cb = 0; cb < p.kb_src[src]; ++cb) {
+            for (int cb = 0; cb < p.kb_src[src]; ++cb, ++kb) {
               ptx::mbar_wait(&ctl->empty[stage], phase ^ 1);
-              uint8_t* sA = smem + stage * stage_bytes;
-              uint8_t* sB = sA + a_bytes;
+              uint8_t* sA = ring + stage * stage_bytes;
               ptx::mbar_arrive_expect_tx(&ctl->full[stage], static_cast<uint32_t>(stage_bytes));
               if (p.mode == 1)
                 ptx::tma_load_4d(sA, &p.tmA[src], &ctl->full[stage], cb * p.BK, x0 + dx, y0 + dy, img);
               else
                 ptx::tma_load_2d(sA, &p.tmA[src], &ctl->full[stage], cb * p.BK, m_tile * kBlockM);
-              const int kcoord = (tap * kb_per_tap + (src ? p.kb_src[0] : 0) + cb) * p.BK;
-              ptx::tma_load_2d(sB, &p.tmB, &ctl->full[stage], kcoord, n_tile * p.BN);
+              if (!resident) ptx::tma_load_2d(sA + a_bytes, &p.tmB, &ctl->full[stage], kb * p.BK, n_tile * p.BN);
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -159,16 +200,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TileIter it(p);
+      if (resident && it.valid()) ptx::mbar_wait(&ctl->b_full, 0);
+      const int ksteps = p.BK / 16;
+      for (; it.valid(); it.next()) {
         ptx::mbar_wait(&ctl->acc_empty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * kAccStride;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&ctl->full[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + a_bytes;
-          const int ksteps = p.BK / 16;
+          const uint32_t a_addr = ptx::smem_u32(ring + stage * stage_bytes);
+          const uint32_t b_addr = resident ? ptx::smem_u32(sBres + kb * b_bytes) : a_addr + a_bytes;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t da = ptx::make_smem_desc(a_addr + k * 32, row_bytes);
             const uint64_t db = ptx::make_smem_desc(b_addr + k * 32, row_bytes);
@@ -189,9 +232,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const Epilogue& e = p.epi;
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.num_n_tiles;
-      const int m_tile = tile / p.num_n_tiles;
+    const int chunks = p.BN / 16;
+    for (TileIter it(p); it.valid(); it.next()) {
+      const int n_tile = it.n_tile(p), m_tile = it.m_tile(p);
       long long orow;  // output row (pixel index or matrix row)
       bool valid;
       if (p.mode == 1) {
@@ -207,43 +250,66 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         valid = orow < p.M;
       }
       const int n0 = n_tile * p.BN;
+      // residual of this thread's row: fetched one chunk ahead of its use so the global-load latency
+      // hides behind the TMEM load / math / stores of the previous chunk
+      const bool has_res = e.res_type != RES_NONE && valid;
+      const char* res_row = nullptr;
+      if (has_res) {
+        const long long rrow = e.res_mod > 0 ? (orow % e.res_mod) : orow;
+        res_row = static_cast<const char*>(e.residual) + (rrow * e.ldr + n0) * (e.res_type == RES_F32 ? 4 : 2);
+      }
+      auto load_res = [&](int ch, ResRegs& rr) {
+        if (!has_res || n0 + ch * 16 >= p.N) return;
+        if (e.res_type == RES_F32) {
+          const uint4* src = reinterpret_cast<const uint4*>(res_row + ch * 64);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rr.u[i] = src[i];
+        } else {
+          const uint4* src = reinterpret_cast<const uint4*>(res_row + ch * 32);
+          rr.u[0] = src[0];
+          rr.u[1] = src[1];
+        }
+      };
+      ResRegs res_next;
+      load_res(half, res_next);
       ptx::mbar_wait(&ctl->acc_full[as], aphase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
-      const int chunks = p.BN / 16;
       for (int ch = half; ch < chunks; ch += 2) {
         uint32_t raw[16];
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the masked stores below
         ptx::tmem_ld16(t_row + ch * 16, raw);
-        ptx::tmem_ld_wait();
+        const ResRegs res = res_next;
+        if (ch + 2 < chunks) load_res(ch + 2, res_next);
         const int col0 = n0 + ch * 16;
-        if (col0 >= p.N) continue;  // warp-uniform
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
-        if (e.bias != nullptr) {
+        float bias[16];
+        if (e.bias != nullptr && col0 < p.N) {
           const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 b = __ldg(b4 + i);
-            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            bias[4 * i + 0] = b.x; bias[4 * i + 1] = b.y; bias[4 * i + 2] = b.z; bias[4 * i + 3] = b.w;
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) bias[i] = 0.f;
         }
-        if (e.res_type != RES_NONE && valid) {
-          const long long rrow = e.res_mod > 0 ? (orow % e.res_mod) : orow;
+        ptx::tmem_ld_wait();
+        if (col0 >= p.N) continue;  // warp-uniform
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) + bias[i];
+        if (has_res) {
           if (e.res_type == RES_F32) {
-            const float4* r4 = reinterpret_cast<const float4*>(static_cast<const float*>(e.residual) + rrow * e.ldr + col0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 b = r4[i];
-              v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+              v[4 * i + 0] += __uint_as_float(res.u[i].x); v[4 * i + 1] += __uint_as_float(res.u[i].y);
+              v[4 * i + 2] += __uint_as_float(res.u[i].z); v[4 * i + 3] += __uint_as_float(res.u[i].w);
             }
           } else {
-            const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(e.residual) + rrow * e.ldr + col0);
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              const uint4 u = r4[i];
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+              const uint32_t w[4] = {res.u[i].x, res.u[i].y, res.u[i].z, res.u[i].w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
@@ -258,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
         } else if (e.act == ACT_GELU) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+          for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
         }
         if (!valid) {
           // masked row (tile overhangs the image / matrix): nothing to store
@@ -379,32 +445,70 @@ int num_sms() {
   return n;
 }
 
-int pick_bn(int N, long long m_tiles) {
-  // largest tile that divides N and still gives every SM a tile; else the largest divisor.
+// Cost model behind the tile-width / schedule choice (cycles per SM, see DESIGN.md "GEMM schedule"):
+//   one k-block of a 128 x BN tile costs max(MMA, operand traffic): MMA = 128*BN*BK/4096 cycles
+//   (tcgen05 cta_group::1 rate), traffic = bytes / ~40 B/cycle/SM (L2 -> SM share with all SMs busy).
+//   Streaming reloads the weight tile for every M tile; weight-resident keeps the CTA's [BN x K]
+//   slice in smem and streams only A.
+struct Plan { int BN; int resident; double cost; };
+
+Plan plan_tiles(int N, int Ktot, int BK, long long m_tiles, bool allow_resident) {
   static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
-  int best = 0;
+  const double kL2 = 40.0;
+  const int sms = num_sms();
+  const int kblocks = Ktot / BK;
+  Plan best{0, 0, 1e300};
   for (int c : cand) {
     if (N % c != 0) continue;
-    if (best == 0) best = c;
-    if (m_tiles * (N / c) >= 2LL * num_sms()) return c;
+    const double mma = 128.0 * c * BK / 4096.0;
+    const double a_bytes = 128.0 * BK * 2, b_bytes = static_cast<double>(c) * BK * 2;
+    const long long n_tiles = N / c;
+    {  // streaming
+      const double tile = kblocks * std::max(mma, (a_bytes + b_bytes) / kL2) + 600.0;
+      const double waves = static_cast<double>((m_tiles * n_tiles + sms - 1) / sms);
+      const double cost = waves * tile;
+      if (cost < best.cost) best = Plan{c, 0, cost};
+    }
+    const long long groups = std::min<long long>(sms / n_tiles, m_tiles);
+    if (allow_resident && n_tiles <= sms && static_cast<long long>(c) * Ktot * 2 <= kResidentMax && groups >= 1 &&
+        m_tiles >= 4 * groups) {
+      const int stages = (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - 1024 - c * Ktot * 2) / (128 * BK * 2);
+      if (stages >= 3) {
+        const double tile = kblocks * std::max(mma, a_bytes / kL2) + 600.0;
+        const double cost = static_cast<double>((m_tiles + groups - 1) / groups) * tile + b_bytes * kblocks / kL2;
+        if (cost < best.cost) best = Plan{c, 1, cost};
+      }
+    }
   }
-  if (best == 0) best = ((N + 15) / 16) * 16 <= 256 ? ((N + 15) / 16) * 16 : 128;
-  // not enough tiles even at the smallest candidate: prefer 128-wide for MMA efficiency
-  for (int c : {128, 96, 64}) if (N % c == 0) return c;
+  if (best.BN == 0) best = Plan{((N + 15) / 16) * 16 <= 256 ? ((N + 15) / 16) * 16 : 128, 0, 0.0};
   return best;
 }
 
 cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   const int row_bytes = kp.BK * 2;
-  const int stage_bytes = kBlockM * row_bytes + kp.BN * row_bytes;
-  kp.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - 1024) / stage_bytes));
-  const size_t smem = static_cast<size_t>(kp.stages) * stage_bytes + sizeof(SmemCtl) + 1024;
+  const int num_kb = kp.taps * (kp.kb_src[0] + kp.kb_src[1]);
+  if (kp.b_resident && (num_kb * kp.BN * row_bytes > kResidentMax || kp.num_n_tiles > num_sms())) kp.b_resident = 0;
+  const int a_bytes = kBlockM * row_bytes, b_bytes = kp.BN * row_bytes;
+  const int res_bytes = kp.b_resident ? num_kb * b_bytes : 0;
+  const int stage_bytes = kp.b_resident ? a_bytes : a_bytes + b_bytes;
+  kp.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - 1024 - res_bytes) / stage_bytes));
+  const size_t smem = static_cast<size_t>(res_bytes) + static_cast<size_t>(kp.stages) * stage_bytes + sizeof(SmemCtl) + 1024;
   TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_tc_kernel), 227 * 1024));
-  const int total = kp.num_m_tiles * kp.num_n_tiles;
-  const int grid = std::min(total, num_sms());
-  prof_record(s, true, 0, 0);
+  int grid;
+  if (kp.b_resident) {
+    const int groups = std::min(num_sms() / kp.num_n_tiles, kp.num_m_tiles);
+    grid = groups * kp.num_n_tiles;
+  } else {
+    grid = std::min(kp.num_m_tiles * kp.num_n_tiles, num_sms());
+  }
+  char tag[112];
+  if (prof_enabled()) {
+    std::snprintf(tag, sizeof(tag), "%s M%d N%d K%d BN%d BK%d st%d grid%d %s", kp.mode ? "conv" : "lin", kp.M, kp.N,
+                  num_kb * kp.BK, kp.BN, kp.BK, kp.stages, grid, kp.b_resident ? "resident" : "stream");
+    prof_record(s, true, 0, 0);
+  }
   gemm_tc_kernel<<<grid, kThreads, smem, s>>>(kp);
-  prof_record(s, false, flops, 0);
+  prof_record(s, false, flops, 0, tag);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -445,7 +549,11 @@ cudaError_t conv_forward(const ConvProblem& c, const Epilogue& e, cudaStream_t s
   kp.num_m_tiles = c.batch * kp.tiles_x * kp.tiles_y;
   kp.N = c.Cout;
   kp.M = c.batch * c.H * c.W;
-  kp.BN = c.BN ? c.BN : pick_bn(c.Cout, kp.num_m_tiles);
+  {
+    const Plan pl = plan_tiles(c.Cout, c.taps * ctot, kp.BK, kp.num_m_tiles, c.resident != 0);
+    kp.BN = c.BN ? c.BN : pl.BN;
+    kp.b_resident = c.BN ? (c.resident == 1) : pl.resident;
+  }
   kp.num_n_tiles = (c.Cout + kp.BN - 1) / kp.BN;
   kp.taps = c.taps; kp.dil = c.dil;
   kp.kb_src[0] = c.src[0].C / kp.BK;
@@ -483,7 +591,11 @@ cudaError_t linear_forward(const LinearProblem& l, const Epilogue& e, cudaStream
   kp.mode = 0;
   kp.M = l.M; kp.N = l.N;
   kp.num_m_tiles = (l.M + kBlockM - 1) / kBlockM;
-  kp.BN = l.BN ? l.BN : pick_bn(l.N, kp.num_m_tiles);
+  {
+    const Plan pl = plan_tiles(l.N, l.K, kp.BK, kp.num_m_tiles, l.resident != 0);
+    kp.BN = l.BN ? l.BN : pl.BN;
+    kp.b_resident = l.BN ? (l.resident == 1) : pl.resident;
+  }
   kp.num_n_tiles = (l.N + kp.BN - 1) / kp.BN;
   kp.taps = 1; kp.dil = 1;
   kp.kb_src[0] = l.K / kp.BK;

@@ -46,6 +46,7 @@ struct ConvProblem {
   const __nv_bfloat16* weight = nullptr;  // [Cout][taps][C0 + C1], K-major
   int Cout = 0;
   int BN = 0;                     // 0 = choose
+  int resident = -1;              // weight-resident schedule: -1 auto, 0 never, 1 force (with BN given)
   int algo_k = 0;                 // true K for FLOP accounting when the stored K is padded (conv1_1: 27)
 };
 
@@ -56,6 +57,7 @@ struct LinearProblem {
   const __nv_bfloat16* W = nullptr;  // [N][K]
   int N = 0;
   int BN = 0;
+  int resident = -1;                 // weight-resident schedule: -1 auto, 0 never, 1 force (with BN given)
   int algo_n = 0;                    // true N for FLOP accounting when N is padded (head: 95)
 };
 
