@@ -83,8 +83,7 @@ def test_conv_weight_resident(native_lib):
         _check(out.reshape(-1, Cout), ref.reshape(-1, Cout), taps * (C0 + C1), f"resident conv {H}x{W} C{C0}+{C1}->{Cout}")
 
 
-@pytest.mark.parametrize("act,res,out_f32", [(1, None, False), (2, None, False), (0, "bf16", False),
-                                             (0, "f32", True), (0, None, True)])
+@pytest.mark.parametrize("act,res,out_f32", [(1, None, False), (2, None, False), (0, "f32", True), (0, None, True)])
 def test_linear_epilogues(native_lib, act, res, out_f32):
     out, ref = _lin(native_lib, 700, 384, 384, act=act, res=res, out_f32=out_f32)
     _check(out, ref, 384, f"linear act{act} res{res} f32{out_f32}")

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -34,8 +35,9 @@ constexpr int kEpiWarps = 8;
 constexpr int kMaxStages = 8;
 constexpr int kAccStride = 256;     // TMEM columns per accumulator stage
 constexpr int kTmemCols = 512;
-constexpr int kSmemBudget = 222 * 1024;
-constexpr int kResidentMax = 144 * 1024;  // largest weight slice kept in smem (BN=192 x K=384 bf16)
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kResidentMax = 64 * 1024;   // largest weight slice kept resident in smem (leaves >= 8 A stages)
+constexpr int kStagingBytes = kEpiWarps * 2048;  // epilogue transpose tiles, 2 KB per warp
 
 struct KParams {
   CUtensorMap tmA[2];
@@ -48,10 +50,12 @@ struct KParams {
   int num_m_tiles, num_n_tiles;
   int stages;
   int b_resident;  // 1: the CTA's [BN x K] weight slice is loaded once and stays in smem; only A streams
+  int debug;       // TT_GEMM_DEBUG (development only): 1 = skip epilogue stores, 2 = skip TMEM loads + math + stores
+  unsigned long long* dbg_out;  // TT_GEMM_DEBUG & 4: per-role wait/busy cycle counters of CTA 0
   Epilogue epi;
 };
 
-struct SmemCtl {
+struct alignas(16) SmemCtl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t acc_full[2];
@@ -59,6 +63,7 @@ struct SmemCtl {
   uint64_t b_full;
   uint32_t tmem_base;
   float tail[16 * 16 + 16 + 2 * 16 + 2];
+  alignas(16) float bias[2][256];  // the tile's bias row, staged per accumulator stage (broadcast reads in the epilogue)
 };
 
 // Tile schedule shared by the three warp roles.  Streaming mode: tiles round-robin over CTAs with the
@@ -107,8 +112,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-struct ResRegs { uint4 u[4]; };  // 16 fp32 or 16 bf16 (first two) residual values of one chunk
-
+// OUT: OUT_BF16 / OUT_F32 / OUT_CLS_TAIL; ACT: ACT_*; RES: fp32 residual added (OUT_F32 only).  The epilogue is
+// specialised at compile time: with these as runtime flags only ~1/4 of its executed instructions were
+// useful work (ncu opcode histogram, profiles/r1_gemm_epilogue.md) and it, not the MMA, set the pace.
+template <int OUT, int ACT, bool RES>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc(&ctl->tmem_base, kTmemCols);
-  if (p.epi.out_type == OUT_CLS_TAIL) {
+  if constexpr (OUT == OUT_CLS_TAIL) {
     for (int i = threadIdx.x; i < 16 * 16 + 16 + 2 * 16 + 2; i += kThreads) ctl->tail[i] = p.epi.tail[i];
   }
   ptx::tc_fence_before();
@@ -162,6 +169,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       int stage = 0;
       uint32_t phase = 0;
+      long long dbg_prod_wait = 0;
+      const long long dbg_t_start = clock64();
       for (; it.valid(); it.next()) {
         const int n_tile = it.n_tile(p), m_tile = it.m_tile(p);
         int img = 0, y0 = 0, x0 = 0;
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const int dx = (p.taps == 9) ? (tap % 3 - 1) * p.dil : 0;
           for (int src = 0; src < 2; ++src) {
             for (int cb = 0; cb < p.kb_src[src]; ++cb, ++kb) {
-              ptx::mbar_wait(&ctl->empty[stage], phase ^ 1);
+              { const long long t0 = clock64(); ptx::mbar_wait(&ctl->empty[stage], phase ^ 1); dbg_prod_wait += clock64() - t0; }
               uint8_t* sA = ring + stage * stage_bytes;
               ptx::mbar_arrive_expect_tx(&ctl->full[stage], static_cast<uint32_t>(stage_bytes));
               if (p.mode == 1)
@@ -191,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
         }
       }
+      if ((p.debug & 4) && blockIdx.x == 0) { p.dbg_out[0] = dbg_prod_wait; p.dbg_out[1] = clock64() - dbg_t_start; }
     }
   } else if (warp == 1) {
     // --------------------------------------------------------------- MMA issuer
@@ -203,12 +213,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       TileIter it(p);
       if (resident && it.valid()) ptx::mbar_wait(&ctl->b_full, 0);
       const int ksteps = p.BK / 16;
+      long long dbg_w_acc = 0, dbg_w_full = 0;
+      const long long dbg_t_start = clock64();
       for (; it.valid(); it.next()) {
-        ptx::mbar_wait(&ctl->acc_empty[as], aphase ^ 1);
+        { const long long t0 = clock64(); ptx::mbar_wait(&ctl->acc_empty[as], aphase ^ 1); dbg_w_acc += clock64() - t0; }
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * kAccStride;
         for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&ctl->full[stage], phase);
+          { const long long t0 = clock64(); ptx::mbar_wait(&ctl->full[stage], phase); dbg_w_full += clock64() - t0; }
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(ring + stage * stage_bytes);
           const uint32_t b_addr = resident ? ptx::smem_u32(sBres + kb * b_bytes) : a_addr + a_bytes;
@@ -223,136 +235,87 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         ptx::mma_commit(&ctl->acc_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
+      if ((p.debug & 4) && blockIdx.x == 0) { p.dbg_out[2] = dbg_w_acc; p.dbg_out[3] = dbg_w_full; p.dbg_out[4] = clock64() - dbg_t_start; }
     }
   } else {
     // ----------------------------------------------------------------- epilogue
-    const int q = warp & 3;             // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;   // two warps share a quadrant, interleaving 16-column chunks
-    const int r = q * 32 + lane;        // tile row == TMEM lane
-    const Epilogue& e = p.epi;
+    // Thread t of a warp owns accumulator row (TMEM lane) q*32 + t, but a row-per-thread global store
+    // touches 32 different cache lines per instruction (measured: it halved the kernel's throughput).
+    // So every 64-byte row segment goes through a warp-private 2 KB smem tile (32 rows x 64 B, 16-byte
+    // units XOR-swizzled): rows are written/read by their owner thread, global memory is accessed with
+    // 4 lanes per row segment, 8 rows per instruction.  Residual reads take the same path backwards.
+    constexpr bool kF32 = OUT == OUT_F32;
+    constexpr int kEsize = kF32 ? 4 : 2;
+    constexpr int kSegChunks = kF32 ? 1 : 2;     // 16-column chunks per 64-byte output segment
+    const int q = warp & 3;                      // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;            // two warps share a quadrant and split the tile's columns
+    const int r = q * 32 + lane;                 // tile row == TMEM lane
+    const uint32_t stg = ptx::smem_u32(reinterpret_cast<uint8_t*>(ctl + 1)) + (warp - 2) * 2048;
+    const uint32_t bias_s = ptx::smem_u32(&ctl->bias[0][0]);
+    const uint32_t own_row = stg + lane * 64;
+    const int own_sw = (lane >> 1) & 3;          // swizzle of this thread's own row
+    const int co_row = lane >> 2, co_unit = lane & 3;  // cooperative access: 4 lanes per row, 8 rows per pass
+    uint32_t co_addr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int row = j * 8 + co_row;
+      co_addr[j] = stg + row * 64 + ((co_unit ^ ((row >> 1) & 3)) << 4);
+    }
+    // hoisted parameters
+    const int BN = p.BN, N = p.N, M = p.M, mode = p.mode, dbg = p.debug & 3;
+    const int H = p.H, W = p.W, TH = p.TH, TW = p.TW, tiles_x = p.tiles_x, per_img = p.tiles_x * p.tiles_y;
+    const long long ldc = p.epi.ldc, ldr = p.epi.ldr;
+    const int res_mod = p.epi.res_mod;
+    char* const out_base = static_cast<char*>(p.epi.out);
+    const char* const res_base = static_cast<const char*>(p.epi.residual);
+    const float* const bias_g = p.epi.bias;
+    const int chunks = BN / 16;
+    const int c_begin = half ? (chunks + 1) / 2 : 0, c_end = half ? chunks : (chunks + 1) / 2;
     int as = 0;
     uint32_t aphase = 0;
-    const int chunks = p.BN / 16;
-    for (TileIter it(p); it.valid(); it.next()) {
-      const int n_tile = it.n_tile(p), m_tile = it.m_tile(p);
-      long long orow;  // output row (pixel index or matrix row)
-      bool valid;
-      if (p.mode == 1) {
-        const int per_img = p.tiles_x * p.tiles_y;
+    long long dbg_e_wait = 0, dbg_e_busy = 0, dbg_tiles = 0;
+    auto row_to_out = [&](int m_tile, int rr, long long& orow) -> bool {
+      if (mode == 1) {
         const int img = m_tile / per_img;
         const int t = m_tile - img * per_img;
-        const int y = (t / p.tiles_x) * p.TH + r / p.TW;
-        const int x = (t % p.tiles_x) * p.TW + r % p.TW;
-        valid = (y < p.H) && (x < p.W);
-        orow = (static_cast<long long>(img) * p.H + y) * p.W + x;
-      } else {
-        orow = static_cast<long long>(m_tile) * kBlockM + r;
-        valid = orow < p.M;
+        const int y = (t / tiles_x) * TH + rr / TW;
+        const int x = (t % tiles_x) * TW + rr % TW;
+        orow = (static_cast<long long>(img) * H + y) * W + x;
+        return (y < H) && (x < W);
       }
-      const int n0 = n_tile * p.BN;
-      // residual of this thread's row: fetched one chunk ahead of its use so the global-load latency
-      // hides behind the TMEM load / math / stores of the previous chunk
-      const bool has_res = e.res_type != RES_NONE && valid;
-      const char* res_row = nullptr;
-      if (has_res) {
-        const long long rrow = e.res_mod > 0 ? (orow % e.res_mod) : orow;
-        res_row = static_cast<const char*>(e.residual) + (rrow * e.ldr + n0) * (e.res_type == RES_F32 ? 4 : 2);
+      orow = static_cast<long long>(m_tile) * kBlockM + rr;
+      return orow < M;
+    };
+    for (TileIter it(p); it.valid(); it.next()) {
+      const int n_tile = it.n_tile(p), m_tile = it.m_tile(p);
+      const int n0 = n_tile * BN;
+      // bias of this tile's columns -> smem (a per-chunk LDG of it was 44% of all stall samples)
+      {
+        const int t = threadIdx.x - 64;  // 0..255 over the epilogue warps
+        const int col = n0 + t;
+        if (t < BN) ptx::sts32(bias_s + (as * 256 + t) * 4, __float_as_uint((bias_g != nullptr && col < N) ? __ldg(bias_g + col) : 0.f));
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
       }
-      auto load_res = [&](int ch, ResRegs& rr) {
-        if (!has_res || n0 + ch * 16 >= p.N) return;
-        if (e.res_type == RES_F32) {
-          const uint4* src = reinterpret_cast<const uint4*>(res_row + ch * 64);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) rr.u[i] = src[i];
-        } else {
-          const uint4* src = reinterpret_cast<const uint4*>(res_row + ch * 32);
-          rr.u[0] = src[0];
-          rr.u[1] = src[1];
-        }
-      };
-      ResRegs res_next;
-      load_res(half, res_next);
-      ptx::mbar_wait(&ctl->acc_full[as], aphase);
-      ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
-      for (int ch = half; ch < chunks; ch += 2) {
-        uint32_t raw[16];
-        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the masked stores below
-        ptx::tmem_ld16(t_row + ch * 16, raw);
-        const ResRegs res = res_next;
-        if (ch + 2 < chunks) load_res(ch + 2, res_next);
-        const int col0 = n0 + ch * 16;
-        float bias[16];
-        if (e.bias != nullptr && col0 < p.N) {
-          const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+      if constexpr (OUT == OUT_CLS_TAIL) {
+        // BN == 16: v = relu(conv 32->16 + b); two 1x1 convs in registers; fp32 [pixel][2] store
+        long long orow;
+        const bool valid = row_to_out(m_tile, r, orow);
+        { const long long t0 = clock64(); ptx::mbar_wait(&ctl->acc_full[as], aphase); dbg_e_wait += clock64() - t0; }
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+        if (half == 0) {
+          uint32_t raw[16];
+          ptx::tmem_ld16(t_row, raw);
+          ptx::tmem_ld_wait(raw);
+          float v[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 b = __ldg(b4 + i);
-            bias[4 * i + 0] = b.x; bias[4 * i + 1] = b.y; bias[4 * i + 2] = b.z; bias[4 * i + 3] = b.w;
+            const uint4 b = ptx::lds128(bias_s + (as * 256 + 4 * i) * 4);
+            v[4 * i + 0] = fmaxf(__uint_as_float(raw[4 * i + 0]) + __uint_as_float(b.x), 0.f);
+            v[4 * i + 1] = fmaxf(__uint_as_float(raw[4 * i + 1]) + __uint_as_float(b.y), 0.f);
+            v[4 * i + 2] = fmaxf(__uint_as_float(raw[4 * i + 2]) + __uint_as_float(b.z), 0.f);
+            v[4 * i + 3] = fmaxf(__uint_as_float(raw[4 * i + 3]) + __uint_as_float(b.w), 0.f);
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) bias[i] = 0.f;
-        }
-        ptx::tmem_ld_wait();
-        if (col0 >= p.N) continue;  // warp-uniform
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) + bias[i];
-        if (has_res) {
-          if (e.res_type == RES_F32) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              v[4 * i + 0] += __uint_as_float(res.u[i].x); v[4 * i + 1] += __uint_as_float(res.u[i].y);
-              v[4 * i + 2] += __uint_as_float(res.u[i].z); v[4 * i + 3] += __uint_as_float(res.u[i].w);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const uint32_t w[4] = {res.u[i].x, res.u[i].y, res.u[i].z, res.u[i].w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-                v[8 * i + 2 * j + 0] += __low2float(h);
-                v[8 * i + 2 * j + 1] += __high2float(h);
-              }
-            }
-          }
-        }
-        if (e.act == ACT_RELU) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
-        } else if (e.act == ACT_GELU) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
-        }
-        if (!valid) {
-          // masked row (tile overhangs the image / matrix): nothing to store
-        } else if (e.out_type == OUT_BF16) {
-          uint4 o0, o1;
-          o0.x = pack_bf16(v[0], v[1]);   o0.y = pack_bf16(v[2], v[3]);
-          o0.z = pack_bf16(v[4], v[5]);   o0.w = pack_bf16(v[6], v[7]);
-          o1.x = pack_bf16(v[8], v[9]);   o1.y = pack_bf16(v[10], v[11]);
-          o1.z = pack_bf16(v[12], v[13]); o1.w = pack_bf16(v[14], v[15]);
-          uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(e.out) + orow * e.ldc + col0);
-          dst[0] = o0;
-          dst[1] = o1;
-          if (e.out2 != nullptr) {
-            uint4* dst2 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(e.out2) + orow * e.ldc + col0);
-            dst2[0] = o0;
-            dst2[1] = o1;
-          }
-        } else if (e.out_type == OUT_F32) {
-          float* dst = static_cast<float*>(e.out) + orow * e.ldc + col0;
-          if (col0 + 16 <= p.N) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            for (int i = 0; i < 16; ++i)
-              if (col0 + i < p.N) dst[i] = v[i];
-          }
-        } else {  // OUT_CLS_TAIL: v = relu(conv 32->16); two 1x1 convs in registers
           const float* w4 = ctl->tail;
           const float* b4 = w4 + 256;
           const float* w5 = b4 + 16;
@@ -371,13 +334,135 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             o0 = fmaf(w5[j], h[j], o0);
             o1 = fmaf(w5[16 + j], h[j], o1);
           }
-          reinterpret_cast<float2*>(e.out)[orow] = make_float2(o0, o1);
+          if (valid) reinterpret_cast<float2*>(out_base)[orow] = make_float2(o0, o1);
         }
+      } else {
+        // the 4 rows this lane touches in the cooperative (coalesced) passes
+        char* co_out[4];
+        const char* co_res[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          long long ro;
+          const bool v = row_to_out(m_tile, q * 32 + j * 8 + co_row, ro);
+          co_out[j] = v ? out_base + (ro * ldc + n0) * kEsize + co_unit * 16 : nullptr;
+          if constexpr (RES) {
+            const long long rrow = res_mod > 0 ? (ro % res_mod) : ro;
+            co_res[j] = v ? res_base + (rrow * ldr + n0) * kEsize + co_unit * 16 : nullptr;
+          }
+        }
+        // columns this lane's 16-byte unit covers inside a segment starting at chunk c0: valid if < N and < c_end
+        const int unit_col = (co_unit * 16) / kEsize;
+        const int unit_chunk = kF32 ? 0 : (co_unit >> 1);
+        uint4 res_next[4];
+        auto load_res = [&](int c0) {
+          const bool ok = (n0 + c0 * 16 + unit_col < N) && (c0 + unit_chunk < c_end);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            res_next[j] = (ok && co_res[j] != nullptr) ? *reinterpret_cast<const uint4*>(co_res[j] + c0 * 16 * kEsize)
+                                                       : make_uint4(0u, 0u, 0u, 0u);
+        };
+        if constexpr (RES) { if (c_begin < c_end) load_res(c_begin); }
+        { const long long t0 = clock64(); ptx::mbar_wait(&ctl->acc_full[as], aphase); dbg_e_wait += clock64() - t0; }
+        const long long dbg_t_busy0 = clock64();
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+        const uint32_t bias_row = bias_s + as * 1024;
+        if (dbg != 2) {
+          // One 64-byte output segment (kSegCols accumulator columns) per step.  Two register sets
+          // alternate so the TMEM load of the next segment is in flight while this one is processed.
+          constexpr int kSegCols = 16 * kSegChunks;
+          auto segment = [&](int c0, uint32_t (&raw)[kSegCols], uint32_t (&nxt)[kSegCols]) {
+            ptx::tmem_ld_wait(raw);
+            if (c0 + kSegChunks < c_end) ptx::tmem_ld<kSegCols>(t_row + (c0 + kSegChunks) * 16, nxt);
+            if (p.debug & 256) {  // bisect: TMEM loads only
+              uint32_t acc = 0;
+#pragma unroll
+              for (int i = 0; i < kSegCols; ++i) acc ^= raw[i];
+              if (acc == 0x12345678u) ptx::sts32(own_row, acc);
+              return;
+            }
+            float resv[16];
+            if constexpr (RES) {  // fp32 residual of this 16-column segment: registers -> smem -> own row
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ptx::sts128(co_addr[j], res_next[j]);
+              __syncwarp();
+              if (c0 + kSegChunks < c_end) load_res(c0 + kSegChunks);  // next segment, in flight during the math
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint4 u = ptx::lds128(own_row + ((k ^ own_sw) << 4));
+                resv[4 * k + 0] = __uint_as_float(u.x); resv[4 * k + 1] = __uint_as_float(u.y);
+                resv[4 * k + 2] = __uint_as_float(u.z); resv[4 * k + 3] = __uint_as_float(u.w);
+              }
+              __syncwarp();
+            }
+#pragma unroll
+            for (int sc = 0; sc < kSegChunks; ++sc) {
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 b = (p.debug & 128) ? make_uint4(0u, 0u, 0u, 0u) : ptx::lds128(bias_row + ((c0 + sc) * 16 + 4 * i) * 4);
+                v[4 * i + 0] = __uint_as_float(raw[sc * 16 + 4 * i + 0]) + __uint_as_float(b.x);
+                v[4 * i + 1] = __uint_as_float(raw[sc * 16 + 4 * i + 1]) + __uint_as_float(b.y);
+                v[4 * i + 2] = __uint_as_float(raw[sc * 16 + 4 * i + 2]) + __uint_as_float(b.z);
+                v[4 * i + 3] = __uint_as_float(raw[sc * 16 + 4 * i + 3]) + __uint_as_float(b.w);
+              }
+              if constexpr (RES) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += resv[i];
+              }
+              if constexpr (ACT == ACT_RELU) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+              } else if constexpr (ACT == ACT_GELU) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
+              }
+              if constexpr (kF32) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  ptx::sts128(own_row + ((k ^ own_sw) << 4),
+                              make_uint4(__float_as_uint(v[4 * k]), __float_as_uint(v[4 * k + 1]),
+                                         __float_as_uint(v[4 * k + 2]), __float_as_uint(v[4 * k + 3])));
+              } else {
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  uint4 o;
+                  o.x = pack_bf16(v[8 * k + 0], v[8 * k + 1]); o.y = pack_bf16(v[8 * k + 2], v[8 * k + 3]);
+                  o.z = pack_bf16(v[8 * k + 4], v[8 * k + 5]); o.w = pack_bf16(v[8 * k + 6], v[8 * k + 7]);
+                  ptx::sts128(own_row + (((sc * 2 + k) ^ own_sw) << 4), o);
+                }
+              }
+            }
+            if (p.debug & 32) return;  // bisect: no cooperative store phase
+            __syncwarp();
+            // coalesced store: 4 lanes x 16 B per row, 8 rows per pass.  (With an odd chunk count the last
+            // bf16 segment's second half holds columns of the neighbouring range: masked by unit_chunk.)
+            const bool ok = (n0 + c0 * 16 + unit_col < N) && (c0 + unit_chunk < c_end) && dbg != 1;
+            const int byte0 = c0 * 16 * kEsize;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 o = ptx::lds128(co_addr[j]);
+              if (ok && co_out[j] != nullptr) *reinterpret_cast<uint4*>(co_out[j] + byte0) = o;
+            }
+            __syncwarp();
+          };
+          uint32_t ra[kSegCols], rb[kSegCols];
+          if (c_begin < c_end) ptx::tmem_ld<kSegCols>(t_row + c_begin * 16, ra);
+          for (int c0 = c_begin; c0 < c_end; c0 += 2 * kSegChunks) {
+            segment(c0, ra, rb);
+            if (c0 + kSegChunks < c_end) segment(c0 + kSegChunks, rb, ra);
+          }
+        }
+        dbg_e_busy += clock64() - dbg_t_busy0;
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&ctl->acc_empty[as]);
+      ++dbg_tiles;
       if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if ((p.debug & 4) && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6)) {
+      p.dbg_out[5 + (warp == 6) * 3] = dbg_e_wait; p.dbg_out[6 + (warp == 6) * 3] = dbg_e_busy; p.dbg_out[7 + (warp == 6) * 3] = dbg_tiles;
     }
   }
 
@@ -472,7 +557,7 @@ Plan plan_tiles(int N, int Ktot, int BK, long long m_tiles, bool allow_resident)
     const long long groups = std::min<long long>(sms / n_tiles, m_tiles);
     if (allow_resident && n_tiles <= sms && static_cast<long long>(c) * Ktot * 2 <= kResidentMax && groups >= 1 &&
         m_tiles >= 4 * groups) {
-      const int stages = (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - 1024 - c * Ktot * 2) / (128 * BK * 2);
+      const int stages = (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - kStagingBytes - 1024 - c * Ktot * 2) / (128 * BK * 2);
       if (stages >= 3) {
         const double tile = kblocks * std::max(mma, a_bytes / kL2) + 600.0;
         const double cost = static_cast<double>((m_tiles + groups - 1) / groups) * tile + b_bytes * kblocks / kL2;
@@ -491,9 +576,17 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   const int a_bytes = kBlockM * row_bytes, b_bytes = kp.BN * row_bytes;
   const int res_bytes = kp.b_resident ? num_kb * b_bytes : 0;
   const int stage_bytes = kp.b_resident ? a_bytes : a_bytes + b_bytes;
-  kp.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - 1024 - res_bytes) / stage_bytes));
-  const size_t smem = static_cast<size_t>(res_bytes) + static_cast<size_t>(kp.stages) * stage_bytes + sizeof(SmemCtl) + 1024;
-  TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_tc_kernel), 227 * 1024));
+  kp.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - kStagingBytes - 1024 - res_bytes) / stage_bytes));
+  const size_t smem = static_cast<size_t>(res_bytes) + static_cast<size_t>(kp.stages) * stage_bytes + sizeof(SmemCtl) + kStagingBytes + 1024;
+  using KernelFn = void (*)(const KParams);
+  KernelFn fn = nullptr;
+  const Epilogue& e = kp.epi;
+  if (e.out_type == OUT_CLS_TAIL) fn = gemm_tc_kernel<OUT_CLS_TAIL, ACT_RELU, false>;
+  else if (e.out_type == OUT_F32) fn = e.res_type == RES_F32 ? gemm_tc_kernel<OUT_F32, ACT_NONE, true> : gemm_tc_kernel<OUT_F32, ACT_NONE, false>;
+  else if (e.act == ACT_RELU) fn = gemm_tc_kernel<OUT_BF16, ACT_RELU, false>;
+  else if (e.act == ACT_GELU) fn = gemm_tc_kernel<OUT_BF16, ACT_GELU, false>;
+  else fn = gemm_tc_kernel<OUT_BF16, ACT_NONE, false>;
+  TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
   int grid;
   if (kp.b_resident) {
     const int groups = std::min(num_sms() / kp.num_n_tiles, kp.num_m_tiles);
@@ -501,15 +594,29 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   } else {
     grid = std::min(kp.num_m_tiles * kp.num_n_tiles, num_sms());
   }
+  static const int dbg = std::getenv("TT_GEMM_DEBUG") ? std::atoi(std::getenv("TT_GEMM_DEBUG")) : 0;
+  kp.debug = dbg;
+  static unsigned long long* dbg_buf = nullptr;
+  if ((dbg & 4) && !dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long));
+  kp.dbg_out = dbg_buf;
+  if (dbg & 4) cudaMemset(dbg_buf, 0, 16 * sizeof(unsigned long long));
   char tag[112];
   if (prof_enabled()) {
     std::snprintf(tag, sizeof(tag), "%s M%d N%d K%d BN%d BK%d st%d grid%d %s", kp.mode ? "conv" : "lin", kp.M, kp.N,
                   num_kb * kp.BK, kp.BN, kp.BK, kp.stages, grid, kp.b_resident ? "resident" : "stream");
     prof_record(s, true, 0, 0);
   }
-  gemm_tc_kernel<<<grid, kThreads, smem, s>>>(kp);
+  fn<<<grid, kThreads, smem, s>>>(kp);
   prof_record(s, false, flops, 0, tag);
   TT_LAUNCH_CHECK();
+  if (dbg & 4) {
+    unsigned long long h[16];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    std::fprintf(stderr, "[gemm dbg] M%d N%d K%d BN%d st%d grid%d | producer wait %llu of %llu | mma wait acc %llu full %llu of %llu | "
+                 "epi w2 wait %llu busy %llu tiles %llu | epi w6 wait %llu busy %llu\n", kp.M, kp.N, num_kb * kp.BK, kp.BN, kp.stages,
+                 grid, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
+  }
   return cudaSuccess;
 }
 
@@ -521,6 +628,18 @@ cudaError_t check_epilogue(const Epilogue& e, int N, int BN) {
   }
   if (e.out_type == OUT_BF16 && (e.ldc % 8 != 0 || N % 16 != 0)) {
     set_error("gemm: bf16 output needs ldc % 8 == 0 and N % 16 == 0");
+    return cudaErrorInvalidValue;
+  }
+  if (e.out_type == OUT_F32 && (e.ldc % 4 != 0 || N % 16 != 0)) {
+    set_error("gemm: fp32 output needs ldc % 4 == 0 and N % 16 == 0");
+    return cudaErrorInvalidValue;
+  }
+  if (e.res_type != RES_NONE && (e.res_type != RES_F32 || e.out_type != OUT_F32 || e.ldr % 4 != 0)) {
+    set_error("gemm: the residual path is fp32 in / fp32 out with a 16-byte aligned pitch");
+    return cudaErrorInvalidValue;
+  }
+  if (e.out_type == OUT_F32 && e.act != ACT_NONE) {
+    set_error("gemm: fp32 output has no fused activation");
     return cudaErrorInvalidValue;
   }
   return cudaSuccess;

@@ -18,14 +18,13 @@ enum OutType : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_CLS_TAIL = 2 };
 struct Epilogue {
   const float* bias = nullptr;      // [N] fp32 (BatchNorm already folded in)
   int act = ACT_NONE;
-  const void* residual = nullptr;   // added after bias, before activation==NONE only
+  const void* residual = nullptr;   // added after bias, before the activation; same element type as `out`
   int res_type = RES_NONE;
   int ldr = 0;                      // residual row pitch (elements)
   int res_mod = 0;                  // >0: residual row = m % res_mod (positional table)
   void* out = nullptr;
   int out_type = OUT_BF16;
   int ldc = 0;                      // output row pitch (elements)
-  void* out2 = nullptr;             // optional second copy of the bf16 output (same pitch)
   // OUT_CLS_TAIL: after bias+ReLU on the 16 accumulators, two 1x1 convs in registers
   // (16->16 ReLU, 16->2) and an fp32 [pixel][2] store.  tail = {w4[16][16], b4[16], w5[2][16], b5[2]}
   const float* tail = nullptr;

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtens
   for (int ch = 0; ch < 8; ++ch) {
     uint32_t raw[16];
     ptx::tmem_ld16(t_row + ch * 16, raw);
-    ptx::tmem_ld_wait();
+    ptx::tmem_ld_wait(raw);
 #pragma unroll
     for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
   }
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtens
   for (int ch = 0; ch < 8; ++ch) {
     uint32_t raw[16];
     ptx::tmem_ld16(t_row + ch * 16, raw);
-    ptx::tmem_ld_wait();
+    ptx::tmem_ld_wait(raw);
     float p[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtens
   for (int ch = 0; ch < 4; ++ch) {
     uint32_t raw[16];
     ptx::tmem_ld16(t_row + ch * 16, raw);
-    ptx::tmem_ld_wait();
+    ptx::tmem_ld_wait(raw);
     float o[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(raw[i]) * inv;
