@@ -148,7 +148,7 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
 
   // crops -> PARSeq, in passes of bounded size; the page buffers stay where they are in the arena,
   // everything CRAFT allocated after them is recycled
-  std::vector<int> all_ids(static_cast<size_t>(n) * d.pd.L);
+  std::vector<int> all_ids(static_cast<size_t>(n) * d.w->pd.L);
   for (int c0 = 0; c0 < n; c0 += kMaxCropsPerPass) {
     const int nc = std::min(kMaxCropsPerPass, n - c0);
     // recycle: keep [pages_dev, craft_in) region by re-reserving on top of it
@@ -180,13 +180,13 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
     if (!refs_dev || !boxes_dev || !patches) { set_error("arena exhausted (crops)"); return 1; }
     E_CUDA(cudaMemcpyAsync(refs_dev, refs.data(), sizeof(PageRef) * B, cudaMemcpyHostToDevice, d.stream));
     E_CUDA(cudaMemcpyAsync(boxes_dev, crops.data() + c0, sizeof(CropBox) * nc, cudaMemcpyHostToDevice, d.stream));
-    g_h2d_bytes += sizeof(PageRef) * B + sizeof(CropBox) * nc + sizeof(int) * nc * d.pd.L /*token init*/;
-    g_d2h_bytes += sizeof(int) * nc * d.pd.L;
+    g_h2d_bytes += sizeof(PageRef) * B + sizeof(CropBox) * nc + sizeof(int) * nc * d.w->pd.L /*token init*/;
+    g_d2h_bytes += sizeof(int) * nc * d.w->pd.L;
     E_TRY(crop_resize(refs_dev, boxes_dev, nc, nullptr, patches, d.stream));
     float* logits = nullptr;
     int* ids = nullptr;
     E_TRY(d.parseq_forward(patches, nc, nullptr, &logits, &ids));
-    E_CUDA(cudaMemcpyAsync(all_ids.data() + static_cast<size_t>(c0) * d.pd.L, ids, sizeof(int) * nc * d.pd.L,
+    E_CUDA(cudaMemcpyAsync(all_ids.data() + static_cast<size_t>(c0) * d.w->pd.L, ids, sizeof(int) * nc * d.w->pd.L,
                            cudaMemcpyDeviceToHost, d.stream));
     E_CUDA(cudaStreamSynchronize(d.stream));
   }
@@ -195,17 +195,18 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
   for (int b = 0; b < B; ++b) {
     PageOut& po = (*results)[idx[b]];
     for (size_t k = 0; k < det[b].size(); ++k, ++c)
-      po.text.push_back(decode_ids(all_ids.data() + static_cast<size_t>(c) * d.pd.L, d.pd.L));
+      po.text.push_back(decode_ids(all_ids.data() + static_cast<size_t>(c) * d.w->pd.L, d.w->pd.L));
   }
   return 0;
 }
 
-int run_device(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const std::vector<int>& mine,
-               const tt_ocr_options& opt, std::vector<PageOut>* results, std::string* err) {
-  std::lock_guard<std::mutex> lock(d.mu);
-  if (cudaSetDevice(d.device) != cudaSuccess) { *err = "cudaSetDevice failed"; return 1; }
+// All pages assigned to one GPU: consecutive pages of identical size form groups of <= max_batch pages;
+// group k runs on slot k % kSlotsPerDevice, the slots run concurrently from their own host threads.
+int run_device(tt_engine& e, int g, const tt_image* pages, const std::vector<int>& mine, const tt_ocr_options& opt,
+               std::vector<PageOut>* results, std::string* err) {
+  const tt_config& cfg = e.cfg;
   const int max_b = cfg.max_batch_pages > 0 ? cfg.max_batch_pages : 8;
-  // group consecutive pages of identical size (the benchmark's pages all are)
+  std::vector<std::vector<int>> groups;
   size_t i = 0;
   while (i < mine.size()) {
     std::vector<int> grp{mine[i]};
@@ -215,9 +216,25 @@ int run_device(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const 
       grp.push_back(mine[j]);
       ++j;
     }
-    if (run_group(d, cfg, pages, grp, opt, results)) { *err = last_error(); return 1; }
+    groups.push_back(std::move(grp));
     i = j;
   }
+  const int S = std::min<int>(kSlotsPerDevice, static_cast<int>(groups.size()));
+  std::vector<int> rcs(S, 0);
+  std::vector<std::string> errs(S);
+  auto slot_main = [&](int sidx) {
+    DeviceCtx& d = *e.devs[g * kSlotsPerDevice + sidx];
+    std::lock_guard<std::mutex> lock(d.mu);
+    if (cudaSetDevice(d.device) != cudaSuccess) { errs[sidx] = "cudaSetDevice failed"; rcs[sidx] = 1; return; }
+    for (size_t k = sidx; k < groups.size(); k += S)
+      if (run_group(d, cfg, pages, groups[k], opt, results)) { errs[sidx] = last_error(); rcs[sidx] = 1; return; }
+  };
+  std::vector<std::thread> th;
+  for (int sidx = 1; sidx < S; ++sidx) th.emplace_back(slot_main, sidx);
+  if (S > 0) slot_main(0);
+  for (auto& t : th) t.join();
+  for (int sidx = 0; sidx < S; ++sidx)
+    if (rcs[sidx]) { *err = errs[sidx]; return 1; }
   return 0;
 }
 
@@ -241,11 +258,16 @@ int tt_engine_create(const char* weights_dir, const int* devices, int n_devices,
     else devs.push_back(0);
     for (int dv : devs) {
       if (dv < 0 || dv >= count) { set_error("invalid device index " + std::to_string(dv)); return 1; }
-      std::unique_ptr<DeviceCtx> d(new DeviceCtx);
-      d->device = dv;
-      if (d->init(weights_dir) != cudaSuccess) return 1;
-      e->devs.push_back(std::move(d));
+      std::shared_ptr<DeviceWeights> shared;
+      for (int sidx = 0; sidx < kSlotsPerDevice; ++sidx) {
+        std::unique_ptr<DeviceCtx> d(new DeviceCtx);
+        d->device = dv;
+        if (d->init(weights_dir, shared) != cudaSuccess) return 1;
+        shared = d->w;
+        e->devs.push_back(std::move(d));
+      }
     }
+    e->n_devices = static_cast<int>(devs.size());
     *out = e.release();
     return 0;
   } catch (const std::exception& ex) {
@@ -257,8 +279,8 @@ int tt_engine_create(const char* weights_dir, const int* devices, int n_devices,
 void tt_engine_destroy(tt_engine* e) { delete e; }
 
 void* tt_engine_stream(tt_engine* e, int idx) {
-  if (!e || idx < 0 || idx >= static_cast<int>(e->devs.size())) return nullptr;
-  return e->devs[idx]->stream;
+  if (!e || idx < 0 || idx >= e->n_devices) return nullptr;
+  return e->devs[idx * kSlotsPerDevice]->stream;
 }
 void tt_io_bytes(unsigned long long* h2d, unsigned long long* d2h) {
   if (h2d) *h2d = g_h2d_bytes.load();
@@ -287,7 +309,7 @@ int tt_ocr_pages_ex(tt_engine* e, const tt_image* pages, int n_pages, const tt_o
         return 1;
       }
     std::vector<PageOut> results(n_pages);
-    const int G = static_cast<int>(e->devs.size());
+    const int G = e->n_devices;
     std::vector<std::vector<int>> shard(G);
     for (int i = 0; i < n_pages; ++i) shard[i % G].push_back(i);  // page i -> GPU i mod G
     std::vector<std::string> errs(G);
@@ -295,11 +317,11 @@ int tt_ocr_pages_ex(tt_engine* e, const tt_image* pages, int n_pages, const tt_o
     std::vector<std::thread> workers;
     for (int g = 0; g < G; ++g) {
       if (shard[g].empty()) continue;
-      workers.emplace_back([&, g] { rcs[g] = run_device(*e->devs[g], e->cfg, pages, shard[g], opt, &results, &errs[g]); });
+      workers.emplace_back([&, g] { rcs[g] = run_device(*e, g, pages, shard[g], opt, &results, &errs[g]); });
     }
     for (auto& w : workers) w.join();
     for (int g = 0; g < G; ++g)
-      if (rcs[g]) { set_error("device " + std::to_string(e->devs[g]->device) + ": " + errs[g]); return 1; }
+      if (rcs[g]) { set_error("device " + std::to_string(e->devs[g * kSlotsPerDevice]->device) + ": " + errs[g]); return 1; }
     // host-side gather into the C result
     tt_result* r = new tt_result;
     r->n_pages = n_pages;
@@ -363,7 +385,7 @@ int tt_parseq_forward(tt_engine* e, const uint8_t* crops, int n, const int32_t* 
     DeviceCtx& d = *e->devs[0];
     std::lock_guard<std::mutex> lock(d.mu);
     E_CUDA(cudaSetDevice(d.device));
-    const int L = d.pd.L, NC = d.pd.n_cls_pad;
+    const int L = d.w->pd.L, NC = d.w->pd.n_cls_pad;
     for (int c0 = 0; c0 < n; c0 += kMaxCropsPerPass) {
       const int nc = std::min(kMaxCropsPerPass, n - c0);
       const size_t crop_bytes = static_cast<size_t>(nc) * 32 * 128 * 3;
@@ -381,8 +403,8 @@ int tt_parseq_forward(tt_engine* e, const uint8_t* crops, int n, const int32_t* 
       int* ids = nullptr;
       E_TRY(d.parseq_forward(patches, nc, forced, &logits, &ids));
       if (logits_out)
-        E_CUDA(cudaMemcpy2DAsync(logits_out + static_cast<size_t>(c0) * L * d.pd.n_cls, sizeof(float) * d.pd.n_cls, logits,
-                                 sizeof(float) * NC, sizeof(float) * d.pd.n_cls, static_cast<size_t>(nc) * L,
+        E_CUDA(cudaMemcpy2DAsync(logits_out + static_cast<size_t>(c0) * L * d.w->pd.n_cls, sizeof(float) * d.w->pd.n_cls, logits,
+                                 sizeof(float) * NC, sizeof(float) * d.w->pd.n_cls, static_cast<size_t>(nc) * L,
                                  cudaMemcpyDeviceToHost, d.stream));
       if (ids_out)
         E_CUDA(cudaMemcpyAsync(ids_out + static_cast<size_t>(c0) * L, ids, sizeof(int) * nc * L, cudaMemcpyDeviceToHost, d.stream));

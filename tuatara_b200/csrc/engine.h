@@ -59,20 +59,33 @@ struct ParseqDims {
   int eos_id = 0, bos_id = 95, pad_id = 96;
 };
 
+// Read-only state shared by the execution slots of one GPU: the two weight files and what is derived from them.
+struct DeviceWeights {
+  int device = 0;
+  WeightFile craft, parseq;
+  ParseqDims pd;
+  float* q_sa_table = nullptr;  // [L][D] fp32: self-attn queries of the 26 positions (crop independent)
+  ~DeviceWeights();
+};
+
+// One execution slot: a stream with its own scratch arena and workspaces.  Each GPU runs kSlotsPerDevice
+// of them from separate host threads so that one slot's host-side phases (box geometry, result
+// assembly, D2H waits) are covered by the other slot's kernels.
+constexpr int kSlotsPerDevice = 2;
+
 struct DeviceCtx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  WeightFile craft, parseq;
-  ParseqDims pd;
+  std::shared_ptr<DeviceWeights> w;
   Arena arena;
-  float* q_sa_table = nullptr;  // [L][D] fp32: self-attn queries of the 26 positions (crop independent)
   PostWorkspace post;           // sized lazily for (batch, H, W)
   uint8_t* pinned = nullptr;    // host staging for D2H of post results / ids
   size_t pinned_bytes = 0;
   std::mutex mu;                // one request at a time per device
 
   ~DeviceCtx();
-  cudaError_t init(const std::string& weights_dir);
+  // shared == nullptr: load the weights; otherwise become another slot on the same GPU
+  cudaError_t init(const std::string& weights_dir, std::shared_ptr<DeviceWeights> shared);
   cudaError_t ensure_pinned(size_t bytes);
   // CRAFT: device u8 [B][H][W][3] (already swapped/padded) -> device fp32 maps [B][H/2][W/2][2] (arena memory)
   cudaError_t craft_forward(const uint8_t* input_dev, int B, int H, int W, float** maps_out);
@@ -87,5 +100,6 @@ struct DeviceCtx {
 
 struct tt_engine {
   tt_config cfg;
-  std::vector<std::unique_ptr<tt::DeviceCtx>> devs;
+  int n_devices = 0;
+  std::vector<std::unique_ptr<tt::DeviceCtx>> devs;  // [device g][slot s] at g * kSlotsPerDevice + s
 };

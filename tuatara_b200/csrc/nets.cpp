@@ -109,18 +109,18 @@ cudaError_t DeviceCtx::craft_forward(const uint8_t* in, int B, int H, int W, flo
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16;
   cudaStream_t s = stream;
 
-  auto conv = [&](const char* name, const bf* a, int Ca, const bf* b, int Cb, int h, int w, int taps, int dil, int cout,
+  auto conv = [&](const char* name, const bf* a, int Ca, const bf* b, int Cb, int hh, int ww, int taps, int dil, int cout,
                   bool relu, bf* out) -> cudaError_t {
     ConvProblem c;
-    c.batch = B; c.H = h; c.W = w;
+    c.batch = B; c.H = hh; c.W = ww;
     c.src[0] = ConvSrc{a, Ca, Ca};
     c.nsrc = 1;
     if (b) { c.src[1] = ConvSrc{b, Cb, Cb}; c.nsrc = 2; }
     c.taps = taps; c.dil = dil; c.Cout = cout;
     if (Ca == 32 && taps == 1 && cout == 64) c.algo_k = 27;  // conv1_1: 3x3x3 taps stored padded to 32
-    c.weight = craft.bf(std::string(name) + ".w");
+    c.weight = w->craft.bf(std::string(name) + ".w");
     Epilogue e;
-    e.bias = craft.f32(std::string(name) + ".b");
+    e.bias = w->craft.f32(std::string(name) + ".b");
     e.act = relu ? ACT_RELU : ACT_NONE;
     e.out = out; e.out_type = OUT_BF16; e.ldc = cout;
     return conv_forward(c, e, s);
@@ -203,12 +203,12 @@ cudaError_t DeviceCtx::craft_forward(const uint8_t* in, int B, int H, int W, flo
     c.batch = B; c.H = H2; c.W = W2;
     c.src[0] = ConvSrc{k2, 32, 32};
     c.taps = 9; c.dil = 1; c.Cout = 16; c.BN = 16;
-    c.weight = craft.bf("cls3.w");
+    c.weight = w->craft.bf("cls3.w");
     Epilogue e;
-    e.bias = craft.f32("cls3.b");
+    e.bias = w->craft.f32("cls3.b");
     e.act = ACT_RELU;
     e.out = maps; e.out_type = OUT_CLS_TAIL; e.ldc = 2;
-    e.tail = craft.f32("cls.tail");
+    e.tail = w->craft.f32("cls.tail");
     RUN(conv_forward(c, e, s));
   }
   *maps_out = maps;
@@ -217,6 +217,7 @@ cudaError_t DeviceCtx::craft_forward(const uint8_t* in, int B, int H, int W, flo
 
 // ---------------------------------------------------------------------------------- PARSeq
 size_t DeviceCtx::parseq_bytes(int n) const {
+  const ParseqDims& pd = w->pd;
   const size_t M = static_cast<size_t>(n) * 128, D = pd.D;
   size_t b = M * D * 4 + M * D * 2 + M * 3 * D * 2 + M * D * 2 + M * pd.mlp * 2 + M * D * 2 + M * 2 * D * 2;  // encoder
   const size_t R = static_cast<size_t>(n) * pd.L;
@@ -239,9 +240,10 @@ static cudaError_t lin(cudaStream_t s, const __nv_bfloat16* A, int lda, int M, i
 cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const int* forced, float** logits_out,
                                       int** ids_out) {
   using bf = __nv_bfloat16;
+  const ParseqDims& pd = w->pd;
+  const WeightFile& wf = w->parseq;
   const int D = pd.D, L = pd.L, M = n * 128, NC = pd.n_cls_pad;
   cudaStream_t s = stream;
-  const WeightFile& w = parseq;
 
   ARENA_GET(x, float, static_cast<size_t>(M) * D);       // fp32 residual stream
   ARENA_GET(h, bf, static_cast<size_t>(M) * D);          // LayerNorm output / attention output
@@ -252,20 +254,20 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
   ARENA_GET(mem_kv, bf, static_cast<size_t>(M) * 2 * D);
 
   // patch embedding (Conv2d k=s=(4,8) as a K=96 GEMM) + bias + pos_embed
-  RUN(lin(s, patches, 96, M, 96, w.bf("pe.w"), D, w.f32("pe.b"), ACT_NONE, w.f32("pos"), RES_F32, D, 128, x, OUT_F32, D));
+  RUN(lin(s, patches, 96, M, 96, wf.bf("pe.w"), D, wf.f32("pe.b"), ACT_NONE, wf.f32("pos"), RES_F32, D, 128, x, OUT_F32, D));
   for (int i = 0; i < pd.depth; ++i) {
     const std::string p = "b" + std::to_string(i) + ".";
-    RUN(layernorm(x, M, D, w.f32(p + "ln1.g"), w.f32(p + "ln1.b"), 1e-6f, h, nullptr, 0, s));
-    RUN(lin(s, h, D, M, D, w.bf(p + "qkv.w"), 3 * D, w.f32(p + "qkv.b"), ACT_NONE, nullptr, RES_NONE, 0, 0, qkv, OUT_BF16, 3 * D));
+    RUN(layernorm(x, M, D, wf.f32(p + "ln1.g"), wf.f32(p + "ln1.b"), 1e-6f, h, nullptr, 0, s));
+    RUN(lin(s, h, D, M, D, wf.bf(p + "qkv.w"), 3 * D, wf.f32(p + "qkv.b"), ACT_NONE, nullptr, RES_NONE, 0, 0, qkv, OUT_BF16, 3 * D));
     RUN(attention_enc(qkv, att, n, D, pd.enc_heads, s));
-    RUN(lin(s, att, D, M, D, w.bf(p + "proj.w"), D, w.f32(p + "proj.b"), ACT_NONE, x, RES_F32, D, 0, x, OUT_F32, D));
-    RUN(layernorm(x, M, D, w.f32(p + "ln2.g"), w.f32(p + "ln2.b"), 1e-6f, h, nullptr, 0, s));
-    RUN(lin(s, h, D, M, D, w.bf(p + "fc1.w"), pd.mlp, w.f32(p + "fc1.b"), ACT_GELU, nullptr, RES_NONE, 0, 0, hid, OUT_BF16, pd.mlp));
-    RUN(lin(s, hid, pd.mlp, M, pd.mlp, w.bf(p + "fc2.w"), D, w.f32(p + "fc2.b"), ACT_NONE, x, RES_F32, D, 0, x, OUT_F32, D));
+    RUN(lin(s, att, D, M, D, wf.bf(p + "proj.w"), D, wf.f32(p + "proj.b"), ACT_NONE, x, RES_F32, D, 0, x, OUT_F32, D));
+    RUN(layernorm(x, M, D, wf.f32(p + "ln2.g"), wf.f32(p + "ln2.b"), 1e-6f, h, nullptr, 0, s));
+    RUN(lin(s, h, D, M, D, wf.bf(p + "fc1.w"), pd.mlp, wf.f32(p + "fc1.b"), ACT_GELU, nullptr, RES_NONE, 0, 0, hid, OUT_BF16, pd.mlp));
+    RUN(lin(s, hid, pd.mlp, M, pd.mlp, wf.bf(p + "fc2.w"), D, wf.f32(p + "fc2.b"), ACT_NONE, x, RES_F32, D, 0, x, OUT_F32, D));
   }
-  RUN(layernorm(x, M, D, w.f32("enc.ln.g"), w.f32("enc.ln.b"), 1e-6f, mem, nullptr, 0, s));
+  RUN(layernorm(x, M, D, wf.f32("enc.ln.g"), wf.f32("enc.ln.b"), 1e-6f, mem, nullptr, 0, s));
   // cross-attention K/V of the memory, once per crop (rows D.. of cross_attn.in_proj)
-  RUN(lin(s, mem, D, M, D, w.bf("dec.ca.in.w") + static_cast<size_t>(D) * D, 2 * D, w.f32("dec.ca.in.b") + D, ACT_NONE,
+  RUN(lin(s, mem, D, M, D, wf.bf("dec.ca.in.w") + static_cast<size_t>(D) * D, 2 * D, wf.f32("dec.ca.in.b") + D, ACT_NONE,
           nullptr, RES_NONE, 0, 0, mem_kv, OUT_BF16, 2 * D));
 
   // ---- decoder: 26 autoregressive steps + one cloze refinement
@@ -287,27 +289,27 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
     TT_CUDA_TRY(cudaMemcpyAsync(tokens, init.data(), sizeof(int) * R, cudaMemcpyHostToDevice, s));
     TT_CUDA_TRY(cudaStreamSynchronize(s));  // `init` is stack-owned
   }
-  const float* posq = w.f32("posq");
+  const float* posq = wf.f32("posq");
   auto stream_tail = [&](const DecoderStep& st, int rows, float* logits_dst, int ldl) -> cudaError_t {
     // t = posq[p] + out_proj(self_attn); t += cross_attn(norm1(t)); t += mlp(norm2(t)); head(norm(t))
-    RUN(dec_self_attn(st, q_sa_table, kv_cache, tokens, pd.eos_id, ab, s));
-    RUN(lin(s, ab, D, rows, D, w.bf("dec.sa.out.w"), D, w.f32("dec.sa.out.b"), ACT_NONE, posq + static_cast<size_t>(st.p0) * D,
+    RUN(dec_self_attn(st, w->q_sa_table, kv_cache, tokens, pd.eos_id, ab, s));
+    RUN(lin(s, ab, D, rows, D, wf.bf("dec.sa.out.w"), D, wf.f32("dec.sa.out.b"), ACT_NONE, posq + static_cast<size_t>(st.p0) * D,
             RES_F32, D, st.np, t, OUT_F32, D));
-    RUN(layernorm(t, rows, D, w.f32("dec.n1.g"), w.f32("dec.n1.b"), 1e-5f, hb, nullptr, 0, s));
-    RUN(lin(s, hb, D, rows, D, w.bf("dec.ca.in.w"), D, w.f32("dec.ca.in.b"), ACT_NONE, nullptr, RES_NONE, 0, 0, qc, OUT_BF16, D));
+    RUN(layernorm(t, rows, D, wf.f32("dec.n1.g"), wf.f32("dec.n1.b"), 1e-5f, hb, nullptr, 0, s));
+    RUN(lin(s, hb, D, rows, D, wf.bf("dec.ca.in.w"), D, wf.f32("dec.ca.in.b"), ACT_NONE, nullptr, RES_NONE, 0, 0, qc, OUT_BF16, D));
     RUN(dec_cross_attn(st, qc, mem_kv, ab, s));
-    RUN(lin(s, ab, D, rows, D, w.bf("dec.ca.out.w"), D, w.f32("dec.ca.out.b"), ACT_NONE, t, RES_F32, D, 0, t, OUT_F32, D));
-    RUN(layernorm(t, rows, D, w.f32("dec.n2.g"), w.f32("dec.n2.b"), 1e-5f, hb, nullptr, 0, s));
-    RUN(lin(s, hb, D, rows, D, w.bf("dec.l1.w"), pd.mlp, w.f32("dec.l1.b"), ACT_GELU, nullptr, RES_NONE, 0, 0, dh, OUT_BF16, pd.mlp));
-    RUN(lin(s, dh, pd.mlp, rows, pd.mlp, w.bf("dec.l2.w"), D, w.f32("dec.l2.b"), ACT_NONE, t, RES_F32, D, 0, t, OUT_F32, D));
-    RUN(layernorm(t, rows, D, w.f32("dec.norm.g"), w.f32("dec.norm.b"), 1e-5f, hb, nullptr, 0, s));
-    RUN(lin(s, hb, D, rows, D, w.bf("head.w"), NC, w.f32("head.b"), ACT_NONE, nullptr, RES_NONE, 0, 0, logits_dst, OUT_F32, ldl));
+    RUN(lin(s, ab, D, rows, D, wf.bf("dec.ca.out.w"), D, wf.f32("dec.ca.out.b"), ACT_NONE, t, RES_F32, D, 0, t, OUT_F32, D));
+    RUN(layernorm(t, rows, D, wf.f32("dec.n2.g"), wf.f32("dec.n2.b"), 1e-5f, hb, nullptr, 0, s));
+    RUN(lin(s, hb, D, rows, D, wf.bf("dec.l1.w"), pd.mlp, wf.f32("dec.l1.b"), ACT_GELU, nullptr, RES_NONE, 0, 0, dh, OUT_BF16, pd.mlp));
+    RUN(lin(s, dh, pd.mlp, rows, pd.mlp, wf.bf("dec.l2.w"), D, wf.f32("dec.l2.b"), ACT_NONE, t, RES_F32, D, 0, t, OUT_F32, D));
+    RUN(layernorm(t, rows, D, wf.f32("dec.norm.g"), wf.f32("dec.norm.b"), 1e-5f, hb, nullptr, 0, s));
+    RUN(lin(s, hb, D, rows, D, wf.bf("head.w"), NC, wf.f32("head.b"), ACT_NONE, nullptr, RES_NONE, 0, 0, logits_dst, OUT_F32, ldl));
     return cudaSuccess;
   };
   for (int i = 0; i < L; ++i) {
     // content K/V of position i joins the cache (rows D.. of self_attn.in_proj = K | V)
-    RUN(dec_context(tokens, w.f32("embed"), posq, w.f32("dec.nc.g"), w.f32("dec.nc.b"), 1e-5f, i, n, D, L, ctx, s));
-    RUN(lin(s, ctx, D, n, D, w.bf("dec.sa.in.w") + static_cast<size_t>(D) * D, 2 * D, w.f32("dec.sa.in.b") + D, ACT_NONE,
+    RUN(dec_context(tokens, wf.f32("embed"), posq, wf.f32("dec.nc.g"), wf.f32("dec.nc.b"), 1e-5f, i, n, D, L, ctx, s));
+    RUN(lin(s, ctx, D, n, D, wf.bf("dec.sa.in.w") + static_cast<size_t>(D) * D, 2 * D, wf.f32("dec.sa.in.b") + D, ACT_NONE,
             nullptr, RES_NONE, 0, 0, kv_cache + static_cast<size_t>(i) * 2 * D, OUT_BF16, L * 2 * D));
     DecoderStep st{n, D, pd.dec_heads, L, i, 1, 0};
     RUN(stream_tail(st, n, logits_ar + static_cast<size_t>(i) * NC, L * NC));
@@ -324,9 +326,13 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
 }
 
 // ------------------------------------------------------------------------------- DeviceCtx
-DeviceCtx::~DeviceCtx() {
+DeviceWeights::~DeviceWeights() {
   cudaSetDevice(device);
   if (q_sa_table) cudaFree(q_sa_table);
+}
+
+DeviceCtx::~DeviceCtx() {
+  cudaSetDevice(device);
   post_workspace_free(&post);
   if (pinned) cudaFreeHost(pinned);
   if (stream) cudaStreamDestroy(stream);
@@ -342,12 +348,19 @@ cudaError_t DeviceCtx::ensure_pinned(size_t bytes) {
   return cudaSuccess;
 }
 
-cudaError_t DeviceCtx::init(const std::string& dir) {
+cudaError_t DeviceCtx::init(const std::string& dir, std::shared_ptr<DeviceWeights> shared) {
   TT_CUDA_TRY(cudaSetDevice(device));
   TT_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  if (shared) {
+    w = std::move(shared);
+    return cudaSuccess;
+  }
+  w = std::make_shared<DeviceWeights>();
+  w->device = device;
+  ParseqDims& pd = w->pd;
   std::vector<int> meta;
-  if (!craft.load(dir + "/craft.ttw")) return cudaErrorInvalidValue;
-  if (!parseq.load(dir + "/parseq.ttw", &meta)) return cudaErrorInvalidValue;
+  if (!w->craft.load(dir + "/craft.ttw")) return cudaErrorInvalidValue;
+  if (!w->parseq.load(dir + "/parseq.ttw", &meta)) return cudaErrorInvalidValue;
   if (meta.size() >= 8) {
     pd.D = meta[0]; pd.depth = meta[1]; pd.enc_heads = meta[2]; pd.dec_heads = meta[3]; pd.mlp = meta[4];
     pd.n_cls = meta[5]; pd.L = meta[6]; pd.n_tok = meta[7];
@@ -356,13 +369,14 @@ cudaError_t DeviceCtx::init(const std::string& dir) {
   }
   if (pd.D != 384) { set_error("only PARSeq-base (embed_dim 384) is built in this round"); return cudaErrorInvalidValue; }
   // self-attention queries: W_q LN_q(pos_queries) + b_q, identical for every crop
-  TT_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&q_sa_table), sizeof(float) * pd.L * pd.D));
+  const WeightFile& wf = w->parseq;
+  TT_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w->q_sa_table), sizeof(float) * pd.L * pd.D));
   TT_CUDA_TRY(arena.reserve(1u << 20));
   arena.reset();
   __nv_bfloat16* qn = arena.get<__nv_bfloat16>(static_cast<size_t>(pd.L) * pd.D);
-  RUN(layernorm(parseq.f32("posq"), pd.L, pd.D, parseq.f32("dec.nq.g"), parseq.f32("dec.nq.b"), 1e-5f, qn, nullptr, 0, stream));
-  RUN(lin(stream, qn, pd.D, pd.L, pd.D, parseq.bf("dec.sa.in.w"), pd.D, parseq.f32("dec.sa.in.b"), ACT_NONE, nullptr,
-          RES_NONE, 0, 0, q_sa_table, OUT_F32, pd.D));
+  RUN(layernorm(wf.f32("posq"), pd.L, pd.D, wf.f32("dec.nq.g"), wf.f32("dec.nq.b"), 1e-5f, qn, nullptr, 0, stream));
+  RUN(lin(stream, qn, pd.D, pd.L, pd.D, wf.bf("dec.sa.in.w"), pd.D, wf.f32("dec.sa.in.b"), ACT_NONE, nullptr,
+          RES_NONE, 0, 0, w->q_sa_table, OUT_F32, pd.D));
   TT_CUDA_TRY(cudaStreamSynchronize(stream));
   return cudaSuccess;
 }

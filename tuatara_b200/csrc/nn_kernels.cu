@@ -322,7 +322,9 @@ __global__ void k_dec_context(const int* __restrict__ tokens, const float* __res
   }
 }
 
-// grid (np, crops), block = heads*32 threads: warp = head, lane = head dim (32)
+// Decoder self-attention.  grid (np, crops), block = heads*32 threads: warp = head.
+// Scores: lane j owns key j (L <= 32 keys): it reads the head's 64 contiguous bytes of K row j and dots
+// them with the query.  Values: lane = head dim, loop over the keys with the probabilities broadcast.
 __global__ void k_dec_self_attn(DecoderStep st, const float* __restrict__ q_table,
                                 const __nv_bfloat16* __restrict__ kv, const int* __restrict__ tokens, int eos_id,
                                 __nv_bfloat16* __restrict__ out) {
@@ -330,79 +332,131 @@ __global__ void k_dec_self_attn(DecoderStep st, const float* __restrict__ q_tabl
   const int p = st.p0 + pi;
   const int head = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = st.D, L = st.L;
-  const float q = q_table[p * D + head * 32 + lane] * 0.17677669529663687f;  // 1/sqrt(32)
-  const __nv_bfloat16* kbase = kv + static_cast<long long>(crop) * L * 2 * D + head * 32 + lane;
+  const __nv_bfloat16* kbase = kv + static_cast<long long>(crop) * L * 2 * D + head * 32;
   // key j allowed?  AR: j <= p.  refine: j != p+1 and no EOS among tokens[1..j]
   int first_eos = L;  // first j >= 1 with tokens[j] == eos
   if (st.refine) {
-    const int t = (lane + 1 < L) ? tokens[crop * L + lane + 1] : -1;  // L <= 33
+    const int t = (lane + 1 < L) ? tokens[crop * L + lane + 1] : -1;  // lane l holds token l+1
     const unsigned m = __ballot_sync(0xffffffffu, t == eos_id);
-    if (m) first_eos = __ffs(m);  // lane l holds token l+1
+    if (m) first_eos = __ffs(m);
   }
-  float my_score = -INFINITY;  // lane j keeps the score of key j
   const int nkeys = st.refine ? L : p + 1;
-  for (int j = 0; j < nkeys; ++j) {
-    const bool ok = st.refine ? (j != p + 1 && j < first_eos) : true;
-    if (!ok) continue;  // warp-uniform
-    float d = q * __bfloat162float(kbase[static_cast<long long>(j) * 2 * D]);
-    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if (lane == j) my_score = d;
-  }
-  float mx = my_score;
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  const float e = (my_score == -INFINITY) ? 0.f : __expf(my_score - mx);
-  float sum = e;
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float pr = e / sum;
-  float acc = 0.f;
-  for (int j = 0; j < nkeys; ++j) {
-    const float pj = __shfl_sync(0xffffffffu, pr, j);
-    if (pj != 0.f) acc += pj * __bfloat162float(kbase[static_cast<long long>(j) * 2 * D + D]);
-  }
-  out[(static_cast<long long>(crop) * st.np + pi) * D + head * 32 + lane] = __float2bfloat16(acc);
-}
-
-// grid (np, crops), block = heads*32: warp = head; 128 memory keys, 4 per lane for the scores
-__global__ void k_dec_cross_attn(DecoderStep st, const __nv_bfloat16* __restrict__ q,
-                                 const __nv_bfloat16* __restrict__ mem_kv, __nv_bfloat16* __restrict__ out) {
-  const int pi = blockIdx.x, crop = blockIdx.y;
-  const int head = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int D = st.D;
-  const long long row = static_cast<long long>(crop) * st.np + pi;
-  // the head's 32 query dims, one per lane, broadcast by shuffle
-  const float qd = __bfloat162float(q[row * D + head * 32 + lane]) * 0.17677669529663687f;
-  const __nv_bfloat16* kv = mem_kv + static_cast<long long>(crop) * 128 * 2 * D + head * 32;
-  float sc[4];
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int key = t * 32 + lane;
-    const uint4* kp = reinterpret_cast<const uint4*>(kv + static_cast<long long>(key) * 2 * D);
+  const bool mine = lane < nkeys && (st.refine ? (lane != p + 1 && lane < first_eos) : true);
+  float score = -INFINITY;
+  if (mine) {
+    const float4* q4 = reinterpret_cast<const float4*>(q_table + p * D + head * 32);
+    const uint4* k4 = reinterpret_cast<const uint4*>(kbase + static_cast<long long>(lane) * 2 * D);
     float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       float f[8];
-      unpack8(__ldg(kp + c), f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc += __shfl_sync(0xffffffffu, qd, c * 8 + i) * f[i];
+      unpack8(__ldg(k4 + c), f);
+      const float4 qa = __ldg(q4 + 2 * c), qb = __ldg(q4 + 2 * c + 1);
+      acc += qa.x * f[0] + qa.y * f[1] + qa.z * f[2] + qa.w * f[3] + qb.x * f[4] + qb.y * f[5] + qb.z * f[6] + qb.w * f[7];
     }
-    sc[t] = acc;
+    score = acc * 0.17677669529663687f;  // 1/sqrt(32)
   }
-  float mx = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+  float mx = score;
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float sum = 0.f;
-#pragma unroll
-  for (int t = 0; t < 4; ++t) { sc[t] = __expf(sc[t] - mx); sum += sc[t]; }
+  const float e = mine ? __expf(score - mx) : 0.f;
+  float sum = e;
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float inv = 1.f / sum;
-  float acc = 0.f;  // lane = output dim
+  const float pr = e / sum;
+  float acc = 0.f;
+  const __nv_bfloat16* vbase = kbase + D + lane;
+  for (int j0 = 0; j0 < nkeys; j0 += 8) {
+    float vv[8];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    for (int l = 0; l < 32; ++l) {
-      const float pj = __shfl_sync(0xffffffffu, sc[t], l);
-      acc += pj * __bfloat162float(kv[static_cast<long long>(t * 32 + l) * 2 * D + D + lane]);
+    for (int u = 0; u < 8; ++u) vv[u] = (j0 + u < nkeys) ? __bfloat162float(vbase[static_cast<long long>(j0 + u) * 2 * D]) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += __shfl_sync(0xffffffffu, pr, (j0 + u) & 31) * vv[u];
+  }
+  out[(static_cast<long long>(crop) * st.np + pi) * D + head * 32 + lane] = __float2bfloat16(acc);
+}
+
+// Decoder cross-attention over the 128 memory tokens of a crop.  grid (np, crops), 12 warps (= heads).
+// Every load is a full coalesced row: a memory row holds K (D bf16) then V (D bf16); a warp takes keys
+// w, w+12, ... and reads each K row as 16-byte units (unit u = head u/4, dims (u%4)*8..+8), dots it with
+// the matching slice of q, reduces over the 4 lanes of a head -> all heads' scores for that key.  After a
+// per-head softmax in smem the V rows are streamed the same way and the 12 warps' partial sums combined.
+__global__ void __launch_bounds__(384) k_dec_cross_attn(DecoderStep st, const __nv_bfloat16* __restrict__ q,
+                                                        const __nv_bfloat16* __restrict__ mem_kv,
+                                                        __nv_bfloat16* __restrict__ out) {
+  constexpr int kD = 384, kHeads = 12, kKeys = 128, kWarps = 12, kUnits = kD / 8;  // 48 16-byte units per K row
+  __shared__ float s_sc[kHeads][kKeys];         // scores, then probabilities
+  __shared__ float s_part[kWarps][kD];          // per-warp partial outputs
+  const int pi = blockIdx.x, crop = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(crop) * st.np + pi;
+  const __nv_bfloat16* kvb = mem_kv + static_cast<long long>(crop) * kKeys * 2 * kD;
+  // q slices for the (up to) two units this lane covers: unit lane, unit 32 + lane (lane < 16)
+  float qa[8], qb[8];
+  unpack8(*reinterpret_cast<const uint4*>(q + row * kD + lane * 8), qa);
+  if (lane < kUnits - 32) unpack8(*reinterpret_cast<const uint4*>(q + row * kD + (32 + lane) * 8), qb);
+  for (int key = warp; key < kKeys; key += kWarps) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(key) * 2 * kD);
+    float f[8];
+    unpack8(__ldg(kr + lane), f);
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += qa[i] * f[i];
+    if (lane < kUnits - 32) {
+      unpack8(__ldg(kr + 32 + lane), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) b += qb[i] * f[i];
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+    b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
+    if ((lane & 3) == 0) {
+      s_sc[lane >> 2][key] = a * 0.17677669529663687f;
+      if (lane < kUnits - 32) s_sc[8 + (lane >> 2)][key] = b * 0.17677669529663687f;
     }
   }
-  out[row * D + head * 32 + lane] = __float2bfloat16(acc * inv);
+  __syncthreads();
+  {  // softmax of head `warp` over the 128 keys
+    float v[4], mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { v[t] = s_sc[warp][t * 32 + lane]; mx = fmaxf(mx, v[t]); }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { v[t] = __expf(v[t] - mx); sum += v[t]; }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) s_sc[warp][t * 32 + lane] = v[t] * inv;
+  }
+  __syncthreads();
+  float oa[8], ob[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { oa[i] = 0.f; ob[i] = 0.f; }
+  for (int key = warp; key < kKeys; key += kWarps) {
+    const uint4* vr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(key) * 2 * kD + kD);
+    float f[8];
+    unpack8(__ldg(vr + lane), f);
+    const float pa = s_sc[lane >> 2][key];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) oa[i] += pa * f[i];
+    if (lane < kUnits - 32) {
+      unpack8(__ldg(vr + 32 + lane), f);
+      const float pb = s_sc[8 + (lane >> 2)][key];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ob[i] += pb * f[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s_part[warp][lane * 8 + i] = oa[i];
+    if (lane < kUnits - 32) s_part[warp][(32 + lane) * 8 + i] = ob[i];
+  }
+  __syncthreads();
+  {
+    const int d = threadIdx.x;  // 384 threads = 384 output dims
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) acc += s_part[w][d];
+    out[row * kD + d] = __float2bfloat16(acc);
+  }
 }
 
 __global__ void k_argmax(const float* __restrict__ logits, int rows, int n_cls, int ld, int* __restrict__ ids,
@@ -505,8 +559,8 @@ cudaError_t dec_self_attn(const DecoderStep& st, const float* q_table, const __n
 cudaError_t dec_cross_attn(const DecoderStep& st, const __nv_bfloat16* q, const __nv_bfloat16* mem_kv,
                            __nv_bfloat16* out, cudaStream_t s) {
   if (st.n_crops <= 0) return cudaSuccess;
-  if (st.D != st.heads * 32) { set_error("dec_cross_attn: head dim must be 32"); return cudaErrorInvalidValue; }
-  k_dec_cross_attn<<<dim3(st.np, st.n_crops), st.heads * 32, 0, s>>>(st, q, mem_kv, out);
+  if (st.D != 384 || st.heads != 12) { set_error("dec_cross_attn: built for D = 384, 12 heads"); return cudaErrorInvalidValue; }
+  k_dec_cross_attn<<<dim3(st.np, st.n_crops), 384, 0, s>>>(st, q, mem_kv, out);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }
