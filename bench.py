@@ -60,10 +60,16 @@ def measured_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def gemm_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), else None."""
+    p = ROOT / "profiles" / "r1_gemm_traffic.json"
+    return json.loads(p.read_text())["dram_bytes_per_launch"] if p.exists() else None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while a timed region runs."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -87,11 +93,19 @@ class ClockSampler:
             except subprocess.TimeoutExpired:
                 self.p.kill()
         self.f.flush()
-        rows = [l.split(",") for l in Path(self.f.name).read_text().splitlines() if l.count(",") >= 7]
+        self.rows = [l.split(",") for l in Path(self.f.name).read_text().splitlines() if l.count(",") >= 7]
         os.unlink(self.f.name)
+
+    def window(self, t0, t1):
+        """Median SM clock / throttle reasons of the samples taken between two datetime marks."""
+        from datetime import datetime
+
         sm, mx, reasons = [], [], set()
-        for r in rows:
+        for r in getattr(self, "rows", []):
             try:
+                ts = datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f")
+                if not (t0 <= ts <= t1):
+                    continue
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except ValueError:
                 continue
@@ -252,10 +266,14 @@ def run_native(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from datetime import datetime
+
+    sampler = ClockSampler(local_rank)  # one nvidia-smi for the whole run (it needs ~1 s to start); windows are cut by time
+    sampler.start()
+
     def timed(step, steps, profile=False):
         barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        w0 = datetime.now()
         l0 = tb.launch_count()
         h0, d0 = C.c_ulonglong(), C.c_ulonglong()
         lib.tt_io_bytes(C.byref(h0), C.byref(d0))
@@ -275,23 +293,29 @@ def run_native(args, rank, local_rank, world):
             pm, pf, pl = C.c_double(), C.c_double(), C.c_ulonglong()
             lib.tt_profile_collect(C.byref(pm), C.byref(pf), C.byref(pl))
             prof = (pm.value, pf.value, pl.value)
-        clocks = sampler.stop()
+        w1 = datetime.now()
         h1, d1 = C.c_ulonglong(), C.c_ulonglong()
         lib.tt_io_bytes(C.byref(h1), C.byref(d1))
         assert items == steps * n * WORDS, f"expected {steps * n * WORDS} items, got {items}"
         return dict(ms=max_over_ranks(ms, world, "cuda"), launches=tb.launch_count() - l0, h2d=(h1.value - h0.value) / steps,
-                    d2h=(d1.value - d0.value) / steps, prof=prof, clocks=clocks)
+                    d2h=(d1.value - d0.value) / steps, prof=prof, window=(w0, w1))
 
     for _ in range(args.warmup):
         step_dev()
-    r_dev = timed(step_dev, args.steps, profile=True)
+    r_dev = timed(step_dev, args.steps)                    # headline: 2 slots per GPU, kernels of two batches interleave
     step_host()
-    r_host = timed(step_host, args.steps)
+    r_host = timed(step_host, args.steps)                  # same through host buffers
+    lib.tt_engine_set_slots(eng._h, 1)                     # roofline pass: one slot => kernels strictly serial, so the
+    step_dev()                                             # per-launch CUDA events measure each launch alone
+    r_prof = timed(step_dev, args.steps, profile=True)
+    lib.tt_engine_set_slots(eng._h, 0)
 
+    sampler.stop()
+    clocks = sampler.window(*r_dev["window"])
     value = job_throughput(n, world, args.steps, r_dev["ms"])
     e2e = job_throughput(n, world, args.steps, r_host["ms"])
     peaks = measured_peaks()
-    pm, pf, pl = r_dev["prof"]
+    pm, pf, pl = r_prof["prof"]
     achieved = pf / (pm / 1e3) / 1e12 if pm > 0 else 0.0
     line = {
         "metric": "pages/sec end-to-end", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
@@ -305,12 +329,14 @@ def run_native(args, rank, local_rank, world):
         "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": r_host["h2d"], "d2h_bytes_per_step": r_host["d2h"],
                 "ms_per_step": r_host["ms"] / args.steps},
         "gpu_launches": int(r_dev["launches"]),
-        "clocks": r_dev["clocks"],
+        "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)",
                      "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tf_sustained"], "traffic": None, "peak_source": peaks["source"],
+                     "frac": achieved / peaks["tf_sustained"], "traffic": gemm_traffic(), "peak_source": peaks["source"],
                      "launches": int(pl), "kernel_ms_per_step": pm / args.steps,
-                     "kernel_share_of_step": pm / r_dev["ms"],
+                     "kernel_share_of_step": pm / r_prof["ms"], "serial_ms_per_step": r_prof["ms"] / args.steps,
+                     "note": "per-launch events from an extra timed pass with one execution slot (serial kernels); "
+                             "the headline value runs two slots per GPU",
                      "algorithmic_gflop_per_step": n * (CRAFT_GFLOP_PER_PAGE + WORDS * PARSEQ_GFLOP_PER_CROP)},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

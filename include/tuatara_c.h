@@ -45,8 +45,8 @@ typedef struct tt_config {
   float link_threshold; /* 0.4   tuatara.cpp:398 */
   float low_text;       /* 0.4   tuatara.cpp:399 */
   int min_area;         /* 10    tuatara.cpp:148 */
-  int max_batch_pages;  /* pages processed per CRAFT batch per GPU (0 = default) */
-  int reserved;
+  int max_batch_pages;  /* pages processed per CRAFT batch per GPU (0 = default 8) */
+  int slots_per_gpu;    /* concurrent execution slots (streams + host threads) per GPU: 0 = default 2, max 2 */
 } tt_config;
 
 typedef struct tt_item {
@@ -90,6 +90,9 @@ TT_API void tt_result_free(tt_result* r);
 /* Kernel launches issued by this library so far (bench.py's gpu_launches). */
 TT_API unsigned long long tt_launch_count(void);
 
+/* Change slots_per_gpu of a live engine (1 = strictly serial kernels: per-launch event timing is only
+ * meaningful then). */
+TT_API void tt_engine_set_slots(tt_engine* e, int slots);
 /* cudaStream_t the engine's idx-th device works on (bench.py records its CUDA events there). */
 TT_API void* tt_engine_stream(tt_engine* e, int idx);
 /* Host<->device bytes moved by tt_ocr_pages* so far (bench.py's h2d/d2h_bytes_per_step). */

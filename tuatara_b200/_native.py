@@ -25,7 +25,7 @@ class tt_image(C.Structure):
 class tt_config(C.Structure):
     _fields_ = [("canvas_size", C.c_float), ("mag_ratio", C.c_float), ("text_threshold", C.c_float),
                 ("link_threshold", C.c_float), ("low_text", C.c_float), ("min_area", C.c_int),
-                ("max_batch_pages", C.c_int), ("reserved", C.c_int)]
+                ("max_batch_pages", C.c_int), ("slots_per_gpu", C.c_int)]
 
 
 class tt_ocr_options(C.Structure):
@@ -61,6 +61,7 @@ SIGNATURES = {
     "tt_ocr_pages_ex": (_I, [_P, C.POINTER(tt_image), _I, C.POINTER(tt_ocr_options), C.POINTER(C.POINTER(tt_result))]),
     "tt_result_free": (None, [C.POINTER(tt_result)]),
     "tt_launch_count": (C.c_ulonglong, []),
+    "tt_engine_set_slots": (None, [_P, _I]),
     "tt_engine_stream": (_P, [_P, _I]),
     "tt_io_bytes": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "tt_profile_enable": (None, [_I]),

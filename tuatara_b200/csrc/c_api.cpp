@@ -68,7 +68,7 @@ void tt_config_default(tt_config* cfg) {
   cfg->low_text = 0.4f;
   cfg->min_area = 10;
   cfg->max_batch_pages = 0;
-  cfg->reserved = 0;
+  cfg->slots_per_gpu = 0;
 }
 
 const char* tt_last_error(void) { return last_error(); }

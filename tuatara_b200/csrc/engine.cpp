@@ -219,7 +219,8 @@ int run_device(tt_engine& e, int g, const tt_image* pages, const std::vector<int
     groups.push_back(std::move(grp));
     i = j;
   }
-  const int S = std::min<int>(kSlotsPerDevice, static_cast<int>(groups.size()));
+  const int want = cfg.slots_per_gpu > 0 ? std::min(cfg.slots_per_gpu, kSlotsPerDevice) : kSlotsPerDevice;
+  const int S = std::min<int>(want, static_cast<int>(groups.size()));
   std::vector<int> rcs(S, 0);
   std::vector<std::string> errs(S);
   auto slot_main = [&](int sidx) {
@@ -277,6 +278,10 @@ int tt_engine_create(const char* weights_dir, const int* devices, int n_devices,
 }
 
 void tt_engine_destroy(tt_engine* e) { delete e; }
+
+void tt_engine_set_slots(tt_engine* e, int slots) {
+  if (e) e->cfg.slots_per_gpu = slots;
+}
 
 void* tt_engine_stream(tt_engine* e, int idx) {
   if (!e || idx < 0 || idx >= e->n_devices) return nullptr;
