@@ -28,10 +28,11 @@ import argparse
 import ctypes as C
 import json
 import os
+import select
 import statistics
 import subprocess
 import sys
-import tempfile
+import threading
 import time
 from pathlib import Path
 
@@ -67,54 +68,99 @@ def gemm_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while a timed region runs."""
+    """SM clock / throttle reasons sampled every 100 ms while the timed regions run.  Same counters as the
+    recipe's `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` line, read through NVML
+    in a thread (nvidia-smi -lms block-buffers its stdout when it is not a tty, so short windows came back
+    empty); falls back to nvidia-smi on a pty when NVML is unavailable."""
 
-    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.rows = []  # (datetime, sm_mhz, max_mhz, set(reasons))
+        self._stop = threading.Event()
+        self._t = None
+        self.source = None
+
+    def _nvml_loop(self, nv, h):
+        from datetime import datetime
+
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.rows.append((datetime.now(), sm, mx, {n for n, bit in self.REASONS if mask & bit}))
+            except Exception:  # noqa: BLE001 - a failed sample is just a missing sample
+                pass
+            self._stop.wait(0.1)
+
+    def _smi_loop(self):
+        import pty
+        from datetime import datetime
+
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        master, slave = pty.openpty()
+        try:
+            p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                  "-i", str(self.gpu)], stdout=slave, stderr=subprocess.DEVNULL)
+        except OSError:
+            return
+        os.close(slave)
+        buf = b""
+        while not self._stop.is_set():
+            r, _, _ = select.select([master], [], [], 0.2)
+            if not r:
+                continue
+            try:
+                buf += os.read(master, 4096)
+            except OSError:
+                break
+            *lines, buf = buf.split(b"\n")
+            for l in lines:
+                f = [x.strip() for x in l.decode(errors="ignore").split(",")]
+                try:
+                    self.rows.append((datetime.now(), float(f[0]), float(f[1]),
+                                      {n for (n, _), v in zip(self.REASONS, f[2:6]) if v.lower() == "active"}))
+                except (ValueError, IndexError):
+                    continue
+        p.terminate()
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "200", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # NVML enumerates by PCI order like nvidia-smi; honour CUDA_VISIBLE_DEVICES remapping
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                ent = vis.split(",")[self.gpu].strip()
+                idx = int(ent) if ent.isdigit() else None
+                h = nv.nvmlDeviceGetHandleByIndex(idx) if idx is not None else nv.nvmlDeviceGetHandleByUUID(ent)
+            else:
+                h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.source = "nvml"
+            self._t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+        except Exception:  # noqa: BLE001
+            self.source = "nvidia-smi"
+            self._t = threading.Thread(target=self._smi_loop, daemon=True)
+        self._t.start()
 
     def stop(self):
-        if self.p is not None:
-            self.p.terminate()
-            try:
-                self.p.wait(timeout=5)
-            except subprocess.TimeoutExpired:
-                self.p.kill()
-        self.f.flush()
-        self.rows = [l.split(",") for l in Path(self.f.name).read_text().splitlines() if l.count(",") >= 7]
-        os.unlink(self.f.name)
+        self._stop.set()
+        if self._t is not None:
+            self._t.join(timeout=5)
 
     def window(self, t0, t1):
         """Median SM clock / throttle reasons of the samples taken between two datetime marks."""
-        from datetime import datetime
-
-        sm, mx, reasons = [], [], set()
-        for r in getattr(self, "rows", []):
-            try:
-                ts = datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f")
-                if not (t0 <= ts <= t1):
-                    continue
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                if v.strip().lower() == "active":
-                    reasons.add(name)
-        if not sm:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
-        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        sel = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not sel:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0, source=self.source)
+        reasons = set().union(*[r[3] for r in sel])
+        return dict(sm_mhz=statistics.median([r[1] for r in sel]), sm_max_mhz=max(r[2] for r in sel),
+                    reasons=sorted(reasons), samples=len(sel), source=self.source)
 
 
 def ensure_weights():

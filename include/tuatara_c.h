@@ -145,7 +145,8 @@ TT_API int tt_rect_to_bbox(const float rect[5], float bbox_out[4]);
 /* --------------------------------------- stage level, device memory (bench / kernel tests) */
 /* out[M][N] = act(A[M][K] * W[N][K]^T + bias) (+ residual). All pointers are device pointers;
  * A, W bf16; bias fp32; out bf16 (out_f32 == 0) or fp32. act: 0 none, 1 relu, 2 gelu.
- * BN: N tile (0 = planner decides); resident: with BN given, 1 = weight-resident schedule. */
+ * BN: N tile (0 = planner decides); resident: schedule flags -- with BN given: bit 0 = weight-resident,
+ * bit 1 = CTA-pair (cta_group::2, 256-row tiles); with BN == 0: 4 = pair forced, 8 = pair forbidden, else planner. */
 TT_API int tt_linear_dev(const void* A, int lda, int M, int K, const void* W, int N, const float* bias, int act,
                   const void* residual, int res_f32, int ldr, void* out, int out_f32, int ldc, int BN, int resident,
                   void* stream);

@@ -70,6 +70,35 @@ def test_linear_weight_resident(native_lib, M, K, N, BN):
     _check(out, ref, K, f"resident linear M{M} K{K} N{N} BN{BN}")
 
 
+@pytest.mark.parametrize("M,K,N,BN,sched", [
+    (256, 64, 256, 256, 2), (128, 64, 64, 64, 2), (100, 384, 1152, 192, 2), (1000, 384, 1152, 192, 2), (4096, 1536, 384, 192, 2),
+    (333, 96, 384, 128, 2), (20000, 384, 1536, 256, 2), (640, 384, 96, 96, 2), (300, 32, 32, 32, 2), (385, 64, 16, 16, 2),
+    (20000, 384, 1536, 256, 3), (131072 + 128, 384, 1152, 192, 3), (70000, 384, 384, 128, 3), (3000, 96, 384, 192, 3),
+    (2400, 384, 768, 256, 3),
+])
+def test_linear_pair(native_lib, M, K, N, BN, sched):
+    """CTA-pair schedule (cta_group::2): 256-row tiles, odd tile counts, streaming (2) and weight-resident (3)."""
+    out, ref = _lin(native_lib, M, K, N, BN=BN, act=2 if N == 1536 else 0, res="f32" if N == 384 else None,
+                    out_f32=(N == 384), resident=sched)
+    _check(out, ref, K, f"pair linear M{M} K{K} N{N} BN{BN} sched{sched}")
+
+
+@pytest.mark.parametrize("act,res,out_f32", [(1, None, False), (2, None, False), (0, "f32", True), (0, None, True)])
+def test_linear_pair_epilogues_auto_bn(native_lib, act, res, out_f32):
+    out, ref = _lin(native_lib, 1700, 384, 384, act=act, res=res, out_f32=out_f32, resident=4)
+    _check(out, ref, 384, f"pair linear act{act} res{res} f32{out_f32}")
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,taps,dil,BN,sched", [
+    (1, 32, 48, 64, 0, 64, 9, 1, 64, 2), (2, 24, 38, 128, 0, 256, 9, 1, 256, 2), (1, 16, 16, 512, 0, 1024, 9, 6, 256, 2),
+    (1, 48, 38, 1024, 512, 512, 1, 1, 256, 2), (1, 64, 64, 32, 0, 32, 9, 1, 32, 3), (3, 8, 8, 256, 128, 128, 1, 1, 128, 2),
+    (3, 40, 24, 64, 0, 64, 9, 1, 64, 3), (1, 8, 16, 64, 0, 128, 9, 1, 128, 2), (5, 24, 24, 128, 0, 128, 9, 1, 0, 4),
+])
+def test_conv_pair(native_lib, B, H, W, C0, C1, Cout, taps, dil, BN, sched):
+    out, ref = _conv(native_lib, B, H, W, C0, C1, Cout, taps, dil, BN=BN, resident=sched)
+    _check(out.reshape(-1, Cout), ref.reshape(-1, Cout), taps * (C0 + C1), f"pair conv {B}x{H}x{W} C{C0}+{C1}->{Cout} t{taps} d{dil} BN{BN} s{sched}")
+
+
 def test_linear_auto_plan_large(native_lib):
     for (M, K, N) in [(131072, 384, 1152), (131072, 1536, 384), (2400, 384, 384), (26 * 300, 384, 96)]:
         out, ref = _lin(native_lib, M, K, N)

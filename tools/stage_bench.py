@@ -23,6 +23,9 @@ def main():
     eng = tb.Engine(wdir, devices=[0])
     stream = torch.cuda.ExternalStream(lib.tt_engine_stream(eng._h, 0))
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    tag = sys.argv[2] if len(sys.argv) > 2 else "full"
+    import os
+    print(f"== {tag}: TT_GEMM_PAIR={os.environ.get('TT_GEMM_PAIR')} TT_ENC_CHUNK={os.environ.get('TT_ENC_CHUNK')}")
     pages = [torch.from_numpy(synth.synth_page(i)).cuda() for i in range(B)]
     maps = [torch.from_numpy(synth.synth_score_maps(i)).cuda() for i in range(B)]
 
@@ -52,11 +55,14 @@ def main():
     full = lambda: eng.ocr_pages(pages, score_override=maps)  # noqa: E731
     t_full = timed(full)
     print(f"full pipeline, {B} pages: {t_full:.2f} ms  ({t_full / B:.3f} ms/page, {B / t_full * 1e3:.1f} pages/s)")
-    ms, fl, n = dump(full, out / "gemm_launches_full.csv")
+    ms, fl, n = dump(full, out / f"gemm_launches_{tag}.csv")
     print(f"  gemm kernel: {n} launches, {ms:.2f} ms, {fl / ms / 1e9:.1f} TFLOP/s")
 
     # CRAFT only / PARSeq only via the stage entry points (host buffers: includes copies, so only the GEMM
     # table is meaningful here)
+    if tag != "full":
+        eng.close()
+        return
     crops = np.random.default_rng(0).integers(0, 256, (1024, 32, 128, 3), dtype=np.uint8)
     pq = lambda: eng.parseq_forward(crops)  # noqa: E731
     t0 = time.perf_counter(); pq(); torch.cuda.synchronize(); t1 = time.perf_counter()

@@ -257,7 +257,8 @@ int tt_linear_dev(const void* A, int lda, int M, int K, const void* W, int N, co
   return guarded([&]() -> int {
     LinearProblem l;
     l.A = static_cast<const __nv_bfloat16*>(A); l.lda = lda; l.M = M; l.K = K;
-    l.W = static_cast<const __nv_bfloat16*>(W); l.N = N; l.BN = BN; l.resident = BN ? resident : -1;
+    l.W = static_cast<const __nv_bfloat16*>(W); l.N = N; l.BN = BN; l.resident = BN ? (resident & 1) : -1;
+    l.pair = BN ? ((resident >> 1) & 1) : ((resident & 4) ? 1 : (resident & 8) ? 0 : -1);
     Epilogue e;
     e.bias = bias; e.act = act;
     e.residual = residual; e.res_type = residual ? (res_f32 ? RES_F32 : RES_BF16) : RES_NONE; e.ldr = ldr;
@@ -276,7 +277,8 @@ int tt_conv_dev(const void* src0, int C0, const void* src1, int C1, int batch, i
     c.nsrc = 1;
     if (src1) { c.src[1] = ConvSrc{static_cast<const __nv_bfloat16*>(src1), C1, C1}; c.nsrc = 2; }
     c.taps = taps; c.dil = dil;
-    c.weight = static_cast<const __nv_bfloat16*>(weight); c.Cout = Cout; c.BN = BN; c.resident = BN ? resident : -1;
+    c.weight = static_cast<const __nv_bfloat16*>(weight); c.Cout = Cout; c.BN = BN; c.resident = BN ? (resident & 1) : -1;
+    c.pair = BN ? ((resident >> 1) & 1) : ((resident & 4) ? 1 : (resident & 8) ? 0 : -1);
     Epilogue e;
     e.bias = bias; e.act = relu ? ACT_RELU : ACT_NONE; e.out = out; e.out_type = OUT_BF16; e.ldc = Cout;
     return conv_forward(c, e, static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : 1;

@@ -5,6 +5,12 @@
 //                                          fp32 accumulators in TMEM, double-buffered (2 x 256 columns)
 //   warps 2..9  epilogue       (8 warps) : tcgen05.ld -> bias / ReLU / GELU / residual / cls tail -> global
 //
+// PAIR mode (cta_group::2): two CTAs of a 2-CTA cluster share one 256 x BN tile.  Each CTA stages its own
+// 128 rows of A and BN/2 rows of the weights, the even CTA issues tcgen05.mma.cta_group::2 for both, each
+// CTA's TMEM holds (and its epilogue drains) its own 128 accumulator rows.  Per-CTA L2->SM operand traffic
+// per MMA cycle drops from (128 + BN) to (128 + BN/2) rows, or to the A rows alone when the CTA's weight
+// half-slice stays resident in smem -- the K=384 PARSeq GEMMs were bound by exactly that traffic.
+//
 // Replaces the ATen conv2d/batch_norm/relu/linear calls the reference reaches through
 // TorchScript at tuatara.cpp:376 (CRAFT) and tuatara.cpp:307 (PARSeq).
 //
@@ -37,6 +43,7 @@ constexpr int kAccStride = 256;     // TMEM columns per accumulator stage
 constexpr int kTmemCols = 512;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kResidentMax = 64 * 1024;   // largest weight slice kept resident in smem (leaves >= 8 A stages)
+constexpr int kResidentMaxPair = 100 * 1024;  // PAIR: half of a 256 x 384 slice (96 KB) + 6 A stages
 constexpr int kStagingBytes = kEpiWarps * 2048;  // epilogue transpose tiles, 2 KB per warp
 
 struct KParams {
@@ -47,7 +54,9 @@ struct KParams {
   int kb_src[2];
   int taps, dil;
   int H, W, TH, TW, tiles_x, tiles_y;
-  int num_m_tiles, num_n_tiles;
+  int num_m_tiles, num_n_tiles;  // num_m_tiles counts scheduling units: 128-row tiles, or 256-row pairs in PAIR mode
+  int m_tiles_total;             // 128-row tiles that exist (PAIR: the last pair may have only one)
+  int pair;
   int stages;
   int b_resident;  // 1: the CTA's [BN x K] weight slice is loaded once and stays in smem; only A streams
   int debug;       // TT_GEMM_DEBUG (development only): 1 = skip epilogue stores, 2 = skip TMEM loads + math + stores
@@ -74,16 +83,18 @@ struct TileIter {
   bool resident;
   __device__ TileIter(const KParams& p) {
     resident = p.b_resident != 0;
+    const int cl = p.pair ? blockIdx.x >> 1 : blockIdx.x;   // scheduling slot: CTA, or CTA pair
+    const int ncl = p.pair ? gridDim.x >> 1 : gridDim.x;
     if (resident) {
-      const int groups = gridDim.x / p.num_n_tiles;
-      n = blockIdx.x % p.num_n_tiles;
-      m = blockIdx.x / p.num_n_tiles;
+      const int groups = ncl / p.num_n_tiles;
+      n = cl % p.num_n_tiles;
+      m = cl / p.num_n_tiles;
       step = groups;
       limit = p.num_m_tiles;
     } else {
-      m = blockIdx.x;  // linear tile index in this mode
+      m = cl;  // linear tile index in this mode
       n = 0;
-      step = gridDim.x;
+      step = ncl;
       limit = p.num_m_tiles * p.num_n_tiles;
     }
   }
@@ -115,14 +126,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // OUT: OUT_BF16 / OUT_F32 / OUT_CLS_TAIL; ACT: ACT_*; RES: fp32 residual added (OUT_F32 only).  The epilogue is
 // specialised at compile time: with these as runtime flags only ~1/4 of its executed instructions were
 // useful work (ncu opcode histogram, profiles/r1_gemm_epilogue.md) and it, not the MMA, set the pace.
-template <int OUT, int ACT, bool RES>
+template <int OUT, int ACT, bool RES, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int row_bytes = p.BK * 2;
   const int a_bytes = kBlockM * row_bytes;
-  const int b_bytes = p.BN * row_bytes;
+  const int b_bytes = (PAIR ? p.BN / 2 : p.BN) * row_bytes;   // this CTA's share of the weight tile
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0;    // 0 = leader (issues the MMAs)
   const int kb_per_tap = p.kb_src[0] + p.kb_src[1];
   const int num_kb = p.taps * kb_per_tap;
   const bool resident = p.b_resident != 0;
@@ -144,17 +156,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&ctl->acc_full[s], 1);
-      ptx::mbar_init(&ctl->acc_empty[s], kEpiWarps);
+      ptx::mbar_init(&ctl->acc_empty[s], PAIR ? 2 * kEpiWarps : kEpiWarps);  // PAIR: both CTAs' epilogues free the leader's
     }
     ptx::mbar_init(&ctl->b_full, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(&ctl->tmem_base, kTmemCols);
+  if (warp == 1) {
+    if constexpr (PAIR) ptx::tmem_alloc_pair(&ctl->tmem_base, kTmemCols);
+    else ptx::tmem_alloc(&ctl->tmem_base, kTmemCols);
+  }
   if constexpr (OUT == OUT_CLS_TAIL) {
     for (int i = threadIdx.x; i < 16 * 16 + 16 + 2 * 16 + 2; i += kThreads) ctl->tail[i] = p.epi.tail[i];
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctl->tmem_base;
 
@@ -162,17 +178,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
       TileIter it(p);
+      const int b_rows = PAIR ? p.BN / 2 : p.BN;
+      const int b_row0 = static_cast<int>(rank) * b_rows;           // this CTA's rows inside the BN-row weight tile
+      const uint32_t tx_mult = PAIR ? 2u : 1u;                      // the leader's barrier counts both CTAs' bytes
+      uint32_t bfull_c = 0, full0_c = 0;                            // PAIR: the leader's barriers as shared::cluster addresses
+      if constexpr (PAIR) {
+        bfull_c = ptx::mapa(ptx::smem_u32(&ctl->b_full), 0);
+        full0_c = ptx::mapa(ptx::smem_u32(&ctl->full[0]), 0);
+      }
       if (resident && it.valid()) {
-        ptx::mbar_arrive_expect_tx(&ctl->b_full, static_cast<uint32_t>(num_kb * b_bytes));
-        for (int kb = 0; kb < num_kb; ++kb)
-          ptx::tma_load_2d(sBres + kb * b_bytes, &p.tmB, &ctl->b_full, kb * p.BK, it.n_tile(p) * p.BN);
+        if (rank == 0) ptx::mbar_arrive_expect_tx(&ctl->b_full, tx_mult * static_cast<uint32_t>(num_kb * b_bytes));
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if constexpr (PAIR) ptx::tma_load_2d_pair(sBres + kb * b_bytes, &p.tmB, bfull_c, kb * p.BK, it.n_tile(p) * p.BN + b_row0);
+          else ptx::tma_load_2d(sBres + kb * b_bytes, &p.tmB, &ctl->b_full, kb * p.BK, it.n_tile(p) * p.BN);
+        }
       }
       int stage = 0;
       uint32_t phase = 0;
       long long dbg_prod_wait = 0;
       const long long dbg_t_start = clock64();
       for (; it.valid(); it.next()) {
-        const int n_tile = it.n_tile(p), m_tile = it.m_tile(p);
+        const int n_tile = it.n_tile(p), m_tile = PAIR ? it.m_tile(p) * 2 + static_cast<int>(rank) : it.m_tile(p);
         int img = 0, y0 = 0, x0 = 0;
         if (p.mode == 1) {
           const int per_img = p.tiles_x * p.tiles_y;
@@ -189,23 +215,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             for (int cb = 0; cb < p.kb_src[src]; ++cb, ++kb) {
               { const long long t0 = clock64(); ptx::mbar_wait(&ctl->empty[stage], phase ^ 1); dbg_prod_wait += clock64() - t0; }
               uint8_t* sA = ring + stage * stage_bytes;
-              ptx::mbar_arrive_expect_tx(&ctl->full[stage], static_cast<uint32_t>(stage_bytes));
-              if (p.mode == 1)
-                ptx::tma_load_4d(sA, &p.tmA[src], &ctl->full[stage], cb * p.BK, x0 + dx, y0 + dy, img);
-              else
-                ptx::tma_load_2d(sA, &p.tmA[src], &ctl->full[stage], cb * p.BK, m_tile * kBlockM);
-              if (!resident) ptx::tma_load_2d(sA + a_bytes, &p.tmB, &ctl->full[stage], kb * p.BK, n_tile * p.BN);
+              if (rank == 0) ptx::mbar_arrive_expect_tx(&ctl->full[stage], tx_mult * static_cast<uint32_t>(stage_bytes));
+              if constexpr (PAIR) {
+                const uint32_t full_bar = full0_c + stage * 8;
+                // a pair's second tile may not exist (odd tile count): its box is out of bounds and arrives as zeros
+                if (p.mode == 1)
+                  ptx::tma_load_4d_pair(sA, &p.tmA[src], full_bar, cb * p.BK, x0 + dx, y0 + dy, img);
+                else
+                  ptx::tma_load_2d_pair(sA, &p.tmA[src], full_bar, cb * p.BK, m_tile * kBlockM);
+                if (!resident) ptx::tma_load_2d_pair(sA + a_bytes, &p.tmB, full_bar, kb * p.BK, n_tile * p.BN + b_row0);
+              } else {
+                if (p.mode == 1)
+                  ptx::tma_load_4d(sA, &p.tmA[src], &ctl->full[stage], cb * p.BK, x0 + dx, y0 + dy, img);
+                else
+                  ptx::tma_load_2d(sA, &p.tmA[src], &ctl->full[stage], cb * p.BK, m_tile * kBlockM);
+                if (!resident) ptx::tma_load_2d(sA + a_bytes, &p.tmB, &ctl->full[stage], kb * p.BK, n_tile * p.BN);
+              }
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
+        }
+      }
+      if constexpr (PAIR) {
+        // drain: the leader's last commits still arrive on this CTA's empty barriers; do not exit before they landed
+        for (int i = 0; i < p.stages; ++i) {
+          ptx::mbar_wait(&ctl->empty[stage], phase ^ 1);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
       if ((p.debug & 4) && blockIdx.x == 0) { p.dbg_out[0] = dbg_prod_wait; p.dbg_out[1] = clock64() - dbg_t_start; }
     }
   } else if (warp == 1) {
     // --------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(kBlockM, p.BN);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, p.BN);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -227,12 +270,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t da = ptx::make_smem_desc(a_addr + k * 32, row_bytes);
             const uint64_t db = ptx::make_smem_desc(b_addr + k * 32, row_bytes);
-            ptx::mma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+            if constexpr (PAIR) ptx::mma_bf16_pair(d_tmem, da, db, idesc, (kb | k) != 0);
+            else ptx::mma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
           }
-          ptx::mma_commit(&ctl->empty[stage]);
+          if constexpr (PAIR) ptx::mma_commit_pair(&ctl->empty[stage], 3);   // frees the stage in both CTAs
+          else ptx::mma_commit(&ctl->empty[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        ptx::mma_commit(&ctl->acc_full[as]);
+        if constexpr (PAIR) ptx::mma_commit_pair(&ctl->acc_full[as], 3);      // both CTAs' epilogues may drain
+        else ptx::mma_commit(&ctl->acc_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
       if ((p.debug & 4) && blockIdx.x == 0) { p.dbg_out[2] = dbg_w_acc; p.dbg_out[3] = dbg_w_full; p.dbg_out[4] = clock64() - dbg_t_start; }
@@ -274,7 +320,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     int as = 0;
     uint32_t aphase = 0;
     long long dbg_e_wait = 0, dbg_e_busy = 0, dbg_tiles = 0;
+    const int m_tiles_total = p.m_tiles_total;
+    const uint32_t acc_empty_leader = PAIR ? ptx::mapa(ptx::smem_u32(&ctl->acc_empty[0]), 0) : 0;
     auto row_to_out = [&](int m_tile, int rr, long long& orow) -> bool {
+      if (PAIR && m_tile >= m_tiles_total) { orow = 0; return false; }
       if (mode == 1) {
         const int img = m_tile / per_img;
         const int t = m_tile - img * per_img;
@@ -287,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       return orow < M;
     };
     for (TileIter it(p); it.valid(); it.next()) {
-      const int n_tile = it.n_tile(p), m_tile = it.m_tile(p);
+      const int n_tile = it.n_tile(p), m_tile = PAIR ? it.m_tile(p) * 2 + static_cast<int>(rank) : it.m_tile(p);
       const int n0 = n_tile * BN;
       // bias of this tile's columns -> smem (a per-chunk LDG of it was 44% of all stall samples)
       {
@@ -457,7 +506,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&ctl->acc_empty[as]);
+      if (lane == 0) {
+        if constexpr (PAIR) ptx::mbar_arrive_cluster(acc_empty_leader + as * 8);
+        else ptx::mbar_arrive(&ctl->acc_empty[as]);
+      }
       ++dbg_tiles;
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -468,9 +520,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync_all();  // neither CTA exits (or frees TMEM) while its peer still works
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -531,82 +585,147 @@ int num_sms() {
 }
 
 // Cost model behind the tile-width / schedule choice (cycles per SM, see DESIGN.md "GEMM schedule"):
-//   one k-block of a 128 x BN tile costs max(MMA, operand traffic): MMA = 128*BN*BK/4096 cycles
-//   (tcgen05 cta_group::1 rate), traffic = bytes / ~40 B/cycle/SM (L2 -> SM share with all SMs busy).
-//   Streaming reloads the weight tile for every M tile; weight-resident keeps the CTA's [BN x K]
-//   slice in smem and streams only A.
-struct Plan { int BN; int resident; double cost; };
+//   one k-block of a tile costs max(MMA, smem operand reads, L2->SM operand traffic):
+//     MMA      = 128*BN*BK/4096 cycles per CTA (tcgen05 rate; a CTA pair computes 256 x BN in the same time),
+//     smem     = operand bytes the CTA's tensor core reads / 128 B/cycle,
+//     traffic  = operand bytes the CTA loads / ~40 B/cycle/SM (L2 -> SM share with all SMs busy:
+//                ~6300 B/cycle chip-wide, B300_MICROARCH.md "LTS throughput cap").
+//   Streaming reloads the weight tile for every M tile; weight-resident keeps the CTA's [rows x K] weight
+//   slice in smem and streams only A.  In PAIR mode a CTA stages BN/2 weight rows instead of BN.
+struct Plan { int BN; int resident; int pair; double cost; };
 
-Plan plan_tiles(int N, int Ktot, int BK, long long m_tiles, bool allow_resident) {
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+Plan plan_tiles(int N, int Ktot, int BK, long long m_tiles, bool allow_resident, int want_pair) {
   static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
-  const double kL2 = 40.0;
+  static const int pair_env = env_int("TT_GEMM_PAIR", 1);  // 0 never, 1 cost model, 2 whenever legal (development)
+  const double kL2 = 40.0, kSmem = 128.0;
   const int sms = num_sms();
   const int kblocks = Ktot / BK;
-  Plan best{0, 0, 1e300};
-  for (int c : cand) {
-    if (N % c != 0) continue;
-    const double mma = 128.0 * c * BK / 4096.0;
-    const double a_bytes = 128.0 * BK * 2, b_bytes = static_cast<double>(c) * BK * 2;
-    const long long n_tiles = N / c;
-    {  // streaming
-      const double tile = kblocks * std::max(mma, (a_bytes + b_bytes) / kL2) + 600.0;
-      const double waves = static_cast<double>((m_tiles * n_tiles + sms - 1) / sms);
-      const double cost = waves * tile;
-      if (cost < best.cost) best = Plan{c, 0, cost};
-    }
-    const long long groups = std::min<long long>(sms / n_tiles, m_tiles);
-    if (allow_resident && n_tiles <= sms && static_cast<long long>(c) * Ktot * 2 <= kResidentMax && groups >= 1 &&
-        m_tiles >= 4 * groups) {
-      const int stages = (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - kStagingBytes - 1024 - c * Ktot * 2) / (128 * BK * 2);
-      if (stages >= 3) {
-        const double tile = kblocks * std::max(mma, a_bytes / kL2) + 600.0;
-        const double cost = static_cast<double>((m_tiles + groups - 1) / groups) * tile + b_bytes * kblocks / kL2;
-        if (cost < best.cost) best = Plan{c, 1, cost};
+  Plan best{0, 0, 0, 1e300};
+  for (int pair = 0; pair < 2; ++pair) {
+    if (pair && (want_pair == 0 || pair_env == 0)) continue;
+    if (!pair && (want_pair == 1 || pair_env == 2) && N % 16 == 0) continue;
+    const long long units = pair ? (m_tiles + 1) / 2 : m_tiles;
+    const int slots = pair ? sms / 2 : sms;
+    const int res_max = pair ? kResidentMaxPair : kResidentMax;
+    for (int c : cand) {
+      if (N % c != 0) continue;
+      const int b_rows = pair ? c / 2 : c;
+      const double mma = 128.0 * c * BK / 4096.0;
+      const double a_bytes = 128.0 * BK * 2, b_bytes = static_cast<double>(b_rows) * BK * 2;
+      const double smem_rd = (a_bytes + b_bytes) / kSmem;
+      const double fixed = pair ? 800.0 : 600.0;
+      const long long n_tiles = N / c;
+      {  // streaming
+        const double tile = kblocks * std::max({mma, smem_rd, (a_bytes + b_bytes) / kL2}) + fixed;
+        const double waves = static_cast<double>((units * n_tiles + slots - 1) / slots);
+        const double cost = waves * tile;
+        if (cost < best.cost) best = Plan{c, 0, pair, cost};
+      }
+      const long long groups = std::min<long long>(slots / n_tiles, units);
+      if (allow_resident && n_tiles <= slots && static_cast<long long>(b_rows) * Ktot * 2 <= res_max && groups >= 1 &&
+          units >= 4 * groups) {
+        const int stages = (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - kStagingBytes - 1024 - b_rows * Ktot * 2) / (128 * BK * 2);
+        if (stages >= 3) {
+          const double tile = kblocks * std::max({mma, smem_rd, a_bytes / kL2}) + fixed;
+          const double cost = static_cast<double>((units + groups - 1) / groups) * tile + b_bytes * kblocks / kL2;
+          if (cost < best.cost) best = Plan{c, 1, pair, cost};
+        }
       }
     }
   }
-  if (best.BN == 0) best = Plan{((N + 15) / 16) * 16 <= 256 ? ((N + 15) / 16) * 16 : 128, 0, 0.0};
+  if (best.BN == 0) best = Plan{((N + 15) / 16) * 16 <= 256 ? ((N + 15) / 16) * 16 : 128, 0, 0, 0.0};
   return best;
 }
 
+// Co-resident CTA pairs the device can hold for this kernel (74 on a full B200: one pair per TPC).
+int max_pairs(const void* fn, size_t smem) {
+  static std::mutex mu;
+  static int cached = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cached) return cached;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * num_sms());
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
+  cached = std::min(n, num_sms() / 2);
+  return cached;
+}
+
+template <bool PAIR>
+void (*select_kernel(const Epilogue& e))(const KParams) {
+  if (e.out_type == OUT_CLS_TAIL) return gemm_tc_kernel<OUT_CLS_TAIL, ACT_RELU, false, PAIR>;
+  if (e.out_type == OUT_F32)
+    return e.res_type == RES_F32 ? gemm_tc_kernel<OUT_F32, ACT_NONE, true, PAIR> : gemm_tc_kernel<OUT_F32, ACT_NONE, false, PAIR>;
+  if (e.act == ACT_RELU) return gemm_tc_kernel<OUT_BF16, ACT_RELU, false, PAIR>;
+  if (e.act == ACT_GELU) return gemm_tc_kernel<OUT_BF16, ACT_GELU, false, PAIR>;
+  return gemm_tc_kernel<OUT_BF16, ACT_NONE, false, PAIR>;
+}
+
+// kp.num_m_tiles holds the 128-row tile count on entry; PAIR mode turns it into the pair count.
 cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   const int row_bytes = kp.BK * 2;
   const int num_kb = kp.taps * (kp.kb_src[0] + kp.kb_src[1]);
-  if (kp.b_resident && (num_kb * kp.BN * row_bytes > kResidentMax || kp.num_n_tiles > num_sms())) kp.b_resident = 0;
-  const int a_bytes = kBlockM * row_bytes, b_bytes = kp.BN * row_bytes;
+  kp.m_tiles_total = kp.num_m_tiles;
+  if (kp.pair && ((kp.BN / 2) % 8 != 0 || kp.epi.out_type == OUT_CLS_TAIL)) kp.pair = 0;
+  if (kp.pair) kp.num_m_tiles = (kp.num_m_tiles + 1) / 2;
+  const int b_rows = kp.pair ? kp.BN / 2 : kp.BN;
+  const int a_bytes = kBlockM * row_bytes, b_bytes = b_rows * row_bytes;
+  using KernelFn = void (*)(const KParams);
+  const KernelFn fn = kp.pair ? select_kernel<true>(kp.epi) : select_kernel<false>(kp.epi);
+  TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
+  const int slots = kp.pair ? max_pairs(reinterpret_cast<const void*>(fn), 200 * 1024) : num_sms();
+  if (kp.b_resident && (num_kb * b_bytes > (kp.pair ? kResidentMaxPair : kResidentMax) || kp.num_n_tiles > slots)) kp.b_resident = 0;
   const int res_bytes = kp.b_resident ? num_kb * b_bytes : 0;
   const int stage_bytes = kp.b_resident ? a_bytes : a_bytes + b_bytes;
   kp.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - kStagingBytes - 1024 - res_bytes) / stage_bytes));
   const size_t smem = static_cast<size_t>(res_bytes) + static_cast<size_t>(kp.stages) * stage_bytes + sizeof(SmemCtl) + kStagingBytes + 1024;
-  using KernelFn = void (*)(const KParams);
-  KernelFn fn = nullptr;
-  const Epilogue& e = kp.epi;
-  if (e.out_type == OUT_CLS_TAIL) fn = gemm_tc_kernel<OUT_CLS_TAIL, ACT_RELU, false>;
-  else if (e.out_type == OUT_F32) fn = e.res_type == RES_F32 ? gemm_tc_kernel<OUT_F32, ACT_NONE, true> : gemm_tc_kernel<OUT_F32, ACT_NONE, false>;
-  else if (e.act == ACT_RELU) fn = gemm_tc_kernel<OUT_BF16, ACT_RELU, false>;
-  else if (e.act == ACT_GELU) fn = gemm_tc_kernel<OUT_BF16, ACT_GELU, false>;
-  else fn = gemm_tc_kernel<OUT_BF16, ACT_NONE, false>;
-  TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
-  int grid;
+  int grid;  // in scheduling slots: CTAs, or CTA pairs
   if (kp.b_resident) {
-    const int groups = std::min(num_sms() / kp.num_n_tiles, kp.num_m_tiles);
+    const int groups = std::min(slots / kp.num_n_tiles, kp.num_m_tiles);
     grid = groups * kp.num_n_tiles;
   } else {
-    grid = std::min(kp.num_m_tiles * kp.num_n_tiles, num_sms());
+    grid = std::min(kp.num_m_tiles * kp.num_n_tiles, slots);
   }
+  if (kp.pair) grid *= 2;
   static const int dbg = std::getenv("TT_GEMM_DEBUG") ? std::atoi(std::getenv("TT_GEMM_DEBUG")) : 0;
   kp.debug = dbg;
   static unsigned long long* dbg_buf = nullptr;
   if ((dbg & 4) && !dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long));
   kp.dbg_out = dbg_buf;
   if (dbg & 4) cudaMemset(dbg_buf, 0, 16 * sizeof(unsigned long long));
-  char tag[112];
+  char tag[128];
   if (prof_enabled()) {
-    std::snprintf(tag, sizeof(tag), "%s M%d N%d K%d BN%d BK%d st%d grid%d %s", kp.mode ? "conv" : "lin", kp.M, kp.N,
-                  num_kb * kp.BK, kp.BN, kp.BK, kp.stages, grid, kp.b_resident ? "resident" : "stream");
+    std::snprintf(tag, sizeof(tag), "%s M%d N%d K%d BN%d BK%d st%d grid%d %s%s", kp.mode ? "conv" : "lin", kp.M, kp.N,
+                  num_kb * kp.BK, kp.BN, kp.BK, kp.stages, grid, kp.b_resident ? "resident" : "stream", kp.pair ? " pair" : "");
     prof_record(s, true, 0, 0);
   }
-  fn<<<grid, kThreads, smem, s>>>(kp);
+  if (kp.pair) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    TT_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, kp));
+  } else {
+    fn<<<grid, kThreads, smem, s>>>(kp);
+  }
   prof_record(s, false, flops, 0, tag);
   TT_LAUNCH_CHECK();
   if (dbg & 4) {
@@ -669,9 +788,11 @@ cudaError_t conv_forward(const ConvProblem& c, const Epilogue& e, cudaStream_t s
   kp.N = c.Cout;
   kp.M = c.batch * c.H * c.W;
   {
-    const Plan pl = plan_tiles(c.Cout, c.taps * ctot, kp.BK, kp.num_m_tiles, c.resident != 0);
+    const Plan pl = plan_tiles(c.Cout, c.taps * ctot, kp.BK, kp.num_m_tiles, c.resident != 0, c.pair);
     kp.BN = c.BN ? c.BN : pl.BN;
     kp.b_resident = c.BN ? (c.resident == 1) : pl.resident;
+    kp.pair = c.BN ? (c.pair == 1) : pl.pair;
+    if (kp.pair && ((kp.BN / 2) % 8 != 0 || e.out_type == OUT_CLS_TAIL)) kp.pair = 0;
   }
   kp.num_n_tiles = (c.Cout + kp.BN - 1) / kp.BN;
   kp.taps = c.taps; kp.dil = c.dil;
@@ -693,7 +814,7 @@ cudaError_t conv_forward(const ConvProblem& c, const Epilogue& e, cudaStream_t s
     const cuuint64_t ktot = static_cast<cuuint64_t>(c.taps) * ctot;
     const cuuint64_t dims[2] = {ktot, static_cast<cuuint64_t>(c.Cout)};
     const cuuint64_t strides[1] = {ktot * 2};
-    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kp.BK), static_cast<cuuint32_t>(kp.BN)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kp.BK), static_cast<cuuint32_t>(kp.pair ? kp.BN / 2 : kp.BN)};
     if (!make_map(&kp.tmB, c.weight, 2, dims, strides, box, row_bytes)) return cudaErrorInvalidValue;
   }
   const double k_algo = c.algo_k > 0 ? c.algo_k : static_cast<double>(c.taps) * ctot;
@@ -711,9 +832,11 @@ cudaError_t linear_forward(const LinearProblem& l, const Epilogue& e, cudaStream
   kp.M = l.M; kp.N = l.N;
   kp.num_m_tiles = (l.M + kBlockM - 1) / kBlockM;
   {
-    const Plan pl = plan_tiles(l.N, l.K, kp.BK, kp.num_m_tiles, l.resident != 0);
+    const Plan pl = plan_tiles(l.N, l.K, kp.BK, kp.num_m_tiles, l.resident != 0, l.pair);
     kp.BN = l.BN ? l.BN : pl.BN;
     kp.b_resident = l.BN ? (l.resident == 1) : pl.resident;
+    kp.pair = l.BN ? (l.pair == 1) : pl.pair;
+    if (kp.pair && ((kp.BN / 2) % 8 != 0 || e.out_type == OUT_CLS_TAIL)) kp.pair = 0;
   }
   kp.num_n_tiles = (l.N + kp.BN - 1) / kp.BN;
   kp.taps = 1; kp.dil = 1;
@@ -732,7 +855,7 @@ cudaError_t linear_forward(const LinearProblem& l, const Epilogue& e, cudaStream
   {
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(l.K), static_cast<cuuint64_t>(l.N)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(l.K) * 2};
-    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kp.BK), static_cast<cuuint32_t>(kp.BN)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kp.BK), static_cast<cuuint32_t>(kp.pair ? kp.BN / 2 : kp.BN)};
     if (!make_map(&kp.tmB, l.W, 2, dims, strides, box, row_bytes)) return cudaErrorInvalidValue;
   }
   return launch(kp, s, 2.0 * l.M * (l.algo_n > 0 ? l.algo_n : l.N) * l.K);

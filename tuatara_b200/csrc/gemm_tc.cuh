@@ -46,6 +46,7 @@ struct ConvProblem {
   int Cout = 0;
   int BN = 0;                     // 0 = choose
   int resident = -1;              // weight-resident schedule: -1 auto, 0 never, 1 force (with BN given)
+  int pair = -1;                  // CTA-pair (cta_group::2, 256-row tiles): -1 auto, 0 never, 1 force
   int algo_k = 0;                 // true K for FLOP accounting when the stored K is padded (conv1_1: 27)
 };
 
@@ -57,6 +58,7 @@ struct LinearProblem {
   int N = 0;
   int BN = 0;
   int resident = -1;                 // weight-resident schedule: -1 auto, 0 never, 1 force (with BN given)
+  int pair = -1;                     // CTA-pair (cta_group::2, 256-row tiles): -1 auto, 0 never, 1 force
   int algo_n = 0;                    // true N for FLOP accounting when N is padded (head: 95)
 };
 

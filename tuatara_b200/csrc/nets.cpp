@@ -2,7 +2,9 @@
 // auxiliary kernels (nn_kernels.cu).  These replace `detector_model.forward` (tuatara.cpp:376) and
 // `model.forward` inside infer() (tuatara.cpp:307); the graphs are the upstream architectures the
 // reference's TorchScript files encode (oracle/models.py is the fp32 oracle).
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
@@ -245,30 +247,43 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
   const int D = pd.D, L = pd.L, M = n * 128, NC = pd.n_cls_pad;
   cudaStream_t s = stream;
 
-  ARENA_GET(x, float, static_cast<size_t>(M) * D);       // fp32 residual stream
-  ARENA_GET(h, bf, static_cast<size_t>(M) * D);          // LayerNorm output / attention output
-  ARENA_GET(qkv, bf, static_cast<size_t>(M) * 3 * D);
-  ARENA_GET(att, bf, static_cast<size_t>(M) * D);
-  ARENA_GET(hid, bf, static_cast<size_t>(M) * pd.mlp);
-  ARENA_GET(mem, bf, static_cast<size_t>(M) * D);
+  // Encoder, in chunks of crops: every intermediate (residual stream, LayerNorm output, qkv, attention
+  // output, MLP hidden) lives in chunk-sized buffers that are reused chunk after chunk, so a producer's
+  // output is still in the 126 MB L2 when its consumer reads it; only the cross-attention K|V of the
+  // memory (what the decoder needs) is written per crop.  At the full batch the same tensors are
+  // 7.5 GB of HBM traffic per block and the encoder is HBM-bound (profiles/r1_launches_a5feb26.md).
+  static const int chunk_env = std::getenv("TT_ENC_CHUNK") ? std::atoi(std::getenv("TT_ENC_CHUNK")) : 0;
+  const int chunk = chunk_env > 0 ? std::min(chunk_env, n) : n;
+  const size_t Mc = static_cast<size_t>(chunk) * 128;
+  ARENA_GET(x, float, Mc * D);       // fp32 residual stream
+  ARENA_GET(h, bf, Mc * D);          // LayerNorm output / attention output
+  ARENA_GET(qkv, bf, Mc * 3 * D);
+  ARENA_GET(att, bf, Mc * D);
+  ARENA_GET(hid, bf, Mc * pd.mlp);
+  ARENA_GET(mem, bf, Mc * D);
   ARENA_GET(mem_kv, bf, static_cast<size_t>(M) * 2 * D);
 
-  // patch embedding (Conv2d k=s=(4,8) as a K=96 GEMM) + bias + pos_embed
-  RUN(lin(s, patches, 96, M, 96, wf.bf("pe.w"), D, wf.f32("pe.b"), ACT_NONE, wf.f32("pos"), RES_F32, D, 128, x, OUT_F32, D));
-  for (int i = 0; i < pd.depth; ++i) {
-    const std::string p = "b" + std::to_string(i) + ".";
-    RUN(layernorm(x, M, D, wf.f32(p + "ln1.g"), wf.f32(p + "ln1.b"), 1e-6f, h, nullptr, 0, s));
-    RUN(lin(s, h, D, M, D, wf.bf(p + "qkv.w"), 3 * D, wf.f32(p + "qkv.b"), ACT_NONE, nullptr, RES_NONE, 0, 0, qkv, OUT_BF16, 3 * D));
-    RUN(attention_enc(qkv, att, n, D, pd.enc_heads, s));
-    RUN(lin(s, att, D, M, D, wf.bf(p + "proj.w"), D, wf.f32(p + "proj.b"), ACT_NONE, x, RES_F32, D, 0, x, OUT_F32, D));
-    RUN(layernorm(x, M, D, wf.f32(p + "ln2.g"), wf.f32(p + "ln2.b"), 1e-6f, h, nullptr, 0, s));
-    RUN(lin(s, h, D, M, D, wf.bf(p + "fc1.w"), pd.mlp, wf.f32(p + "fc1.b"), ACT_GELU, nullptr, RES_NONE, 0, 0, hid, OUT_BF16, pd.mlp));
-    RUN(lin(s, hid, pd.mlp, M, pd.mlp, wf.bf(p + "fc2.w"), D, wf.f32(p + "fc2.b"), ACT_NONE, x, RES_F32, D, 0, x, OUT_F32, D));
+  for (int c0 = 0; c0 < n; c0 += chunk) {
+    const int nc = std::min(chunk, n - c0);
+    const int Mi = nc * 128;
+    const bf* pch = patches + static_cast<size_t>(c0) * 128 * 96;
+    // patch embedding (Conv2d k=s=(4,8) as a K=96 GEMM) + bias + pos_embed
+    RUN(lin(s, pch, 96, Mi, 96, wf.bf("pe.w"), D, wf.f32("pe.b"), ACT_NONE, wf.f32("pos"), RES_F32, D, 128, x, OUT_F32, D));
+    for (int i = 0; i < pd.depth; ++i) {
+      const std::string p = "b" + std::to_string(i) + ".";
+      RUN(layernorm(x, Mi, D, wf.f32(p + "ln1.g"), wf.f32(p + "ln1.b"), 1e-6f, h, nullptr, 0, s));
+      RUN(lin(s, h, D, Mi, D, wf.bf(p + "qkv.w"), 3 * D, wf.f32(p + "qkv.b"), ACT_NONE, nullptr, RES_NONE, 0, 0, qkv, OUT_BF16, 3 * D));
+      RUN(attention_enc(qkv, att, nc, D, pd.enc_heads, s));
+      RUN(lin(s, att, D, Mi, D, wf.bf(p + "proj.w"), D, wf.f32(p + "proj.b"), ACT_NONE, x, RES_F32, D, 0, x, OUT_F32, D));
+      RUN(layernorm(x, Mi, D, wf.f32(p + "ln2.g"), wf.f32(p + "ln2.b"), 1e-6f, h, nullptr, 0, s));
+      RUN(lin(s, h, D, Mi, D, wf.bf(p + "fc1.w"), pd.mlp, wf.f32(p + "fc1.b"), ACT_GELU, nullptr, RES_NONE, 0, 0, hid, OUT_BF16, pd.mlp));
+      RUN(lin(s, hid, pd.mlp, Mi, pd.mlp, wf.bf(p + "fc2.w"), D, wf.f32(p + "fc2.b"), ACT_NONE, x, RES_F32, D, 0, x, OUT_F32, D));
+    }
+    RUN(layernorm(x, Mi, D, wf.f32("enc.ln.g"), wf.f32("enc.ln.b"), 1e-6f, mem, nullptr, 0, s));
+    // cross-attention K/V of the memory, once per crop (rows D.. of cross_attn.in_proj)
+    RUN(lin(s, mem, D, Mi, D, wf.bf("dec.ca.in.w") + static_cast<size_t>(D) * D, 2 * D, wf.f32("dec.ca.in.b") + D, ACT_NONE,
+            nullptr, RES_NONE, 0, 0, mem_kv + static_cast<size_t>(c0) * 128 * 2 * D, OUT_BF16, 2 * D));
   }
-  RUN(layernorm(x, M, D, wf.f32("enc.ln.g"), wf.f32("enc.ln.b"), 1e-6f, mem, nullptr, 0, s));
-  // cross-attention K/V of the memory, once per crop (rows D.. of cross_attn.in_proj)
-  RUN(lin(s, mem, D, M, D, wf.bf("dec.ca.in.w") + static_cast<size_t>(D) * D, 2 * D, wf.f32("dec.ca.in.b") + D, ACT_NONE,
-          nullptr, RES_NONE, 0, 0, mem_kv, OUT_BF16, 2 * D));
 
   // ---- decoder: 26 autoregressive steps + one cloze refinement
   const int R = n * L;
