@@ -36,15 +36,14 @@ namespace tt {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kThreads = 320;       // 10 warps
-constexpr int kEpiWarps = 8;
+constexpr int kMaxEpiWarps = 16;    // epilogue warps: 8 (fp32 / residual outputs) or 16 (bf16 outputs), template parameter EW
 constexpr int kMaxStages = 8;
 constexpr int kAccStride = 256;     // TMEM columns per accumulator stage
 constexpr int kTmemCols = 512;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kResidentMax = 64 * 1024;   // largest weight slice kept resident in smem (leaves >= 8 A stages)
 constexpr int kResidentMaxPair = 100 * 1024;  // PAIR: half of a 256 x 384 slice (96 KB) + 6 A stages
-constexpr int kStagingBytes = kEpiWarps * 2048;  // epilogue transpose tiles, 2 KB per warp
+constexpr int kStagingBytes = kMaxEpiWarps * 2048;  // epilogue transpose tiles, 2 KB per warp (upper bound, used for planning)
 
 struct KParams {
   CUtensorMap tmA[2];
@@ -118,6 +117,50 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
+// Packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2): one issue slot per two elements.  With two epilogue warps
+// per scheduler the epilogue, not the tensor pipe, set the pace of the K=384 GEMMs (ncu: 14.5 warp instructions
+// per output element, issue slots 50 % busy, tensor pipe 37 %; profiles/r1b_gemm_fc1.md).
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// gelu_fast on two elements at once
+__device__ __forceinline__ uint64_t gelu_fast2(uint64_t x) {
+  float a, b;
+  upk2(mul2(x, x), a, b);
+  const uint64_t x2 = pk2(fminf(a, 36.0f), fminf(b, 36.0f));
+  uint64_t p = fma2(x2, pk2(-0.00035151678866f, -0.00035151678866f), pk2(0.037005646023f, 0.037005646023f));
+  p = fma2(x2, p, pk2(0.797507884285f, 0.797507884285f));
+  upk2(mul2(x, p), a, b);
+  float ta, tb;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(a));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(b));
+  const uint64_t hx = mul2(x, pk2(0.5f, 0.5f));
+  return fma2(hx, pk2(ta, tb), hx);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -126,8 +169,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // OUT: OUT_BF16 / OUT_F32 / OUT_CLS_TAIL; ACT: ACT_*; RES: fp32 residual added (OUT_F32 only).  The epilogue is
 // specialised at compile time: with these as runtime flags only ~1/4 of its executed instructions were
 // useful work (ncu opcode histogram, profiles/r1_gemm_epilogue.md) and it, not the MMA, set the pace.
-template <int OUT, int ACT, bool RES, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ KParams p) {
+template <int OUT, int ACT, bool RES, bool PAIR, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_constant__ KParams p) {
+  constexpr int kThreads = 64 + 32 * EW;
+  constexpr int kEpiWarps = EW;
+  constexpr int kParts = EW / 4;   // warps sharing a TMEM lane quadrant split the tile's columns
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -294,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     constexpr int kEsize = kF32 ? 4 : 2;
     constexpr int kSegChunks = kF32 ? 1 : 2;     // 16-column chunks per 64-byte output segment
     const int q = warp & 3;                      // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;            // two warps share a quadrant and split the tile's columns
+    const int part = (warp - 2) >> 2;            // kParts warps share a quadrant and split the tile's columns
     const int r = q * 32 + lane;                 // tile row == TMEM lane
     const uint32_t stg = ptx::smem_u32(reinterpret_cast<uint8_t*>(ctl + 1)) + (warp - 2) * 2048;
     const uint32_t bias_s = ptx::smem_u32(&ctl->bias[0][0]);
@@ -316,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const char* const res_base = static_cast<const char*>(p.epi.residual);
     const float* const bias_g = p.epi.bias;
     const int chunks = BN / 16;
-    const int c_begin = half ? (chunks + 1) / 2 : 0, c_end = half ? chunks : (chunks + 1) / 2;
+    const int c_begin = (chunks * part + kParts - 1) / kParts, c_end = (chunks * (part + 1) + kParts - 1) / kParts;
     int as = 0;
     uint32_t aphase = 0;
     long long dbg_e_wait = 0, dbg_e_busy = 0, dbg_tiles = 0;
@@ -335,15 +381,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       orow = static_cast<long long>(m_tile) * kBlockM + rr;
       return orow < M;
     };
-    for (TileIter it(p); it.valid(); it.next()) {
+    // bias of a tile's columns -> smem (a per-chunk LDG of it was 44% of all stall samples); the value for the
+    // NEXT tile is fetched while this one is processed (its LDG latency was 9% of the samples after that).
+    const int bias_t = threadIdx.x - 64;  // 0 .. 32*EW-1 over the epilogue warps
+    auto bias_fetch = [&](const TileIter& t) -> float {
+      const int col0 = t.n_tile(p) * BN + bias_t, col1 = col0 + 32 * EW;
+      (void)col1;
+      return (t.valid() && bias_g != nullptr && bias_t < BN && col0 < N) ? __ldg(bias_g + col0) : 0.f;
+    };
+    TileIter it(p);
+    float bias_cur = bias_fetch(it);
+    for (; it.valid(); it.next()) {
       const int n_tile = it.n_tile(p), m_tile = PAIR ? it.m_tile(p) * 2 + static_cast<int>(rank) : it.m_tile(p);
       const int n0 = n_tile * BN;
-      // bias of this tile's columns -> smem (a per-chunk LDG of it was 44% of all stall samples)
       {
-        const int t = threadIdx.x - 64;  // 0..255 over the epilogue warps
-        const int col = n0 + t;
-        if (t < BN) ptx::sts32(bias_s + (as * 256 + t) * 4, __float_as_uint((bias_g != nullptr && col < N) ? __ldg(bias_g + col) : 0.f));
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
+        if (bias_t < BN) ptx::sts32(bias_s + (as * 256 + bias_t) * 4, __float_as_uint(bias_cur));
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");  // epilogue warps only
+        TileIter nx = it;
+        nx.next();
+        bias_cur = bias_fetch(nx);
       }
       if constexpr (OUT == OUT_CLS_TAIL) {
         // BN == 16: v = relu(conv 32->16 + b); two 1x1 convs in registers; fp32 [pixel][2] store
@@ -352,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         { const long long t0 = clock64(); ptx::mbar_wait(&ctl->acc_full[as], aphase); dbg_e_wait += clock64() - t0; }
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
-        if (half == 0) {
+        if (part == 0) {
           uint32_t raw[16];
           ptx::tmem_ld16(t_row, raw);
           ptx::tmem_ld_wait(raw);
@@ -420,16 +476,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           // One 64-byte output segment (kSegCols accumulator columns) per step.  Two register sets
           // alternate so the TMEM load of the next segment is in flight while this one is processed.
           constexpr int kSegCols = 16 * kSegChunks;
-          auto segment = [&](int c0, uint32_t (&raw)[kSegCols], uint32_t (&nxt)[kSegCols]) {
+          auto segment = [&](int c0, uint32_t (&raw)[kSegCols], uint32_t (&nxt)[kSegCols], bool prefetch) {
             ptx::tmem_ld_wait(raw);
-            if (c0 + kSegChunks < c_end) ptx::tmem_ld<kSegCols>(t_row + (c0 + kSegChunks) * 16, nxt);
-            if (p.debug & 256) {  // bisect: TMEM loads only
-              uint32_t acc = 0;
-#pragma unroll
-              for (int i = 0; i < kSegCols; ++i) acc ^= raw[i];
-              if (acc == 0x12345678u) ptx::sts32(own_row, acc);
-              return;
-            }
+            if (prefetch && c0 + kSegChunks < c_end) ptx::tmem_ld<kSegCols>(t_row + (c0 + kSegChunks) * 16, nxt);
             float resv[16];
             if constexpr (RES) {  // fp32 residual of this 16-column segment: registers -> smem -> own row
 #pragma unroll
@@ -446,25 +495,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
 #pragma unroll
             for (int sc = 0; sc < kSegChunks; ++sc) {
-              float v[16];
+              uint64_t v2[8];  // 16 columns as fp32 pairs (packed FADD2/FFMA2: half the issue slots)
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const uint4 b = (p.debug & 128) ? make_uint4(0u, 0u, 0u, 0u) : ptx::lds128(bias_row + ((c0 + sc) * 16 + 4 * i) * 4);
-                v[4 * i + 0] = __uint_as_float(raw[sc * 16 + 4 * i + 0]) + __uint_as_float(b.x);
-                v[4 * i + 1] = __uint_as_float(raw[sc * 16 + 4 * i + 1]) + __uint_as_float(b.y);
-                v[4 * i + 2] = __uint_as_float(raw[sc * 16 + 4 * i + 2]) + __uint_as_float(b.z);
-                v[4 * i + 3] = __uint_as_float(raw[sc * 16 + 4 * i + 3]) + __uint_as_float(b.w);
+                const uint4 b = ptx::lds128(bias_row + ((c0 + sc) * 16 + 4 * i) * 4);
+                v2[2 * i] = add2(pk2u(raw[sc * 16 + 4 * i + 0], raw[sc * 16 + 4 * i + 1]), pk2u(b.x, b.y));
+                v2[2 * i + 1] = add2(pk2u(raw[sc * 16 + 4 * i + 2], raw[sc * 16 + 4 * i + 3]), pk2u(b.z, b.w));
               }
               if constexpr (RES) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += resv[i];
+                for (int i = 0; i < 8; ++i) v2[i] = add2(v2[i], pk2(resv[2 * i], resv[2 * i + 1]));
               }
+              if constexpr (ACT == ACT_GELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v2[i] = gelu_fast2(v2[i]);
+              }
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) upk2(v2[i], v[2 * i], v[2 * i + 1]);
               if constexpr (ACT == ACT_RELU) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
-              } else if constexpr (ACT == ACT_GELU) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
               }
               if constexpr (kF32) {
 #pragma unroll
@@ -482,7 +533,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 }
               }
             }
-            if (p.debug & 32) return;  // bisect: no cooperative store phase
             __syncwarp();
             // coalesced store: 4 lanes x 16 B per row, 8 rows per pass.  (With an odd chunk count the last
             // bf16 segment's second half holds columns of the neighbouring range: masked by unit_chunk.)
@@ -495,11 +545,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
             __syncwarp();
           };
-          uint32_t ra[kSegCols], rb[kSegCols];
-          if (c_begin < c_end) ptx::tmem_ld<kSegCols>(t_row + c_begin * 16, ra);
-          for (int c0 = c_begin; c0 < c_end; c0 += 2 * kSegChunks) {
-            segment(c0, ra, rb);
-            if (c0 + kSegChunks < c_end) segment(c0 + kSegChunks, rb, ra);
+          if constexpr (EW == 8) {
+            uint32_t ra[kSegCols], rb[kSegCols];
+            if (c_begin < c_end) ptx::tmem_ld<kSegCols>(t_row + c_begin * 16, ra);
+            for (int c0 = c_begin; c0 < c_end; c0 += 2 * kSegChunks) {
+              segment(c0, ra, rb, true);
+              if (c0 + kSegChunks < c_end) segment(c0 + kSegChunks, rb, ra, true);
+            }
+          } else {
+            // 4 warps per scheduler hide the TMEM load latency; one register set keeps the 576-thread CTA under 112 registers
+            uint32_t ra[kSegCols];
+            for (int c0 = c_begin; c0 < c_end; c0 += kSegChunks) {
+              ptx::tmem_ld<kSegCols>(t_row + c0 * 16, ra);
+              segment(c0, ra, ra, false);
+            }
           }
         }
         dbg_e_busy += clock64() - dbg_t_busy0;
@@ -643,14 +702,14 @@ Plan plan_tiles(int N, int Ktot, int BK, long long m_tiles, bool allow_resident,
 }
 
 // Co-resident CTA pairs the device can hold for this kernel (74 on a full B200: one pair per TPC).
-int max_pairs(const void* fn, size_t smem) {
+int max_pairs(const void* fn, size_t smem, int threads) {
   static std::mutex mu;
   static int cached = 0;
   std::lock_guard<std::mutex> lock(mu);
   if (cached) return cached;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * num_sms());
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -663,14 +722,27 @@ int max_pairs(const void* fn, size_t smem) {
   return cached;
 }
 
+// Epilogue warps per CTA: 16 for the bf16-output kernels (their epilogue instruction stream set the pace with 8),
+// 8 for the fp32 / residual ones (HBM-bound) and the CRAFT head.  TT_GEMM_EW=8 forces 8 everywhere (development).
+int epi_warps(const Epilogue& e) {
+  static const int ew_env = env_int("TT_GEMM_EW", 0);
+  if (ew_env == 8) return 8;
+  return e.out_type == OUT_BF16 ? 16 : 8;
+}
+
 template <bool PAIR>
 void (*select_kernel(const Epilogue& e))(const KParams) {
-  if (e.out_type == OUT_CLS_TAIL) return gemm_tc_kernel<OUT_CLS_TAIL, ACT_RELU, false, PAIR>;
+  if (e.out_type == OUT_CLS_TAIL) return gemm_tc_kernel<OUT_CLS_TAIL, ACT_RELU, false, PAIR, 8>;
   if (e.out_type == OUT_F32)
-    return e.res_type == RES_F32 ? gemm_tc_kernel<OUT_F32, ACT_NONE, true, PAIR> : gemm_tc_kernel<OUT_F32, ACT_NONE, false, PAIR>;
-  if (e.act == ACT_RELU) return gemm_tc_kernel<OUT_BF16, ACT_RELU, false, PAIR>;
-  if (e.act == ACT_GELU) return gemm_tc_kernel<OUT_BF16, ACT_GELU, false, PAIR>;
-  return gemm_tc_kernel<OUT_BF16, ACT_NONE, false, PAIR>;
+    return e.res_type == RES_F32 ? gemm_tc_kernel<OUT_F32, ACT_NONE, true, PAIR, 8> : gemm_tc_kernel<OUT_F32, ACT_NONE, false, PAIR, 8>;
+  if (epi_warps(e) == 8) {
+    if (e.act == ACT_RELU) return gemm_tc_kernel<OUT_BF16, ACT_RELU, false, PAIR, 8>;
+    if (e.act == ACT_GELU) return gemm_tc_kernel<OUT_BF16, ACT_GELU, false, PAIR, 8>;
+    return gemm_tc_kernel<OUT_BF16, ACT_NONE, false, PAIR, 8>;
+  }
+  if (e.act == ACT_RELU) return gemm_tc_kernel<OUT_BF16, ACT_RELU, false, PAIR, 16>;
+  if (e.act == ACT_GELU) return gemm_tc_kernel<OUT_BF16, ACT_GELU, false, PAIR, 16>;
+  return gemm_tc_kernel<OUT_BF16, ACT_NONE, false, PAIR, 16>;
 }
 
 // kp.num_m_tiles holds the 128-row tile count on entry; PAIR mode turns it into the pair count.
@@ -685,12 +757,14 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   using KernelFn = void (*)(const KParams);
   const KernelFn fn = kp.pair ? select_kernel<true>(kp.epi) : select_kernel<false>(kp.epi);
   TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
-  const int slots = kp.pair ? max_pairs(reinterpret_cast<const void*>(fn), 200 * 1024) : num_sms();
+  const int threads = 64 + 32 * epi_warps(kp.epi);
+  const int staging = epi_warps(kp.epi) * 2048;
+  const int slots = kp.pair ? max_pairs(reinterpret_cast<const void*>(fn), 200 * 1024, threads) : num_sms();
   if (kp.b_resident && (num_kb * b_bytes > (kp.pair ? kResidentMaxPair : kResidentMax) || kp.num_n_tiles > slots)) kp.b_resident = 0;
   const int res_bytes = kp.b_resident ? num_kb * b_bytes : 0;
   const int stage_bytes = kp.b_resident ? a_bytes : a_bytes + b_bytes;
-  kp.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - kStagingBytes - 1024 - res_bytes) / stage_bytes));
-  const size_t smem = static_cast<size_t>(res_bytes) + static_cast<size_t>(kp.stages) * stage_bytes + sizeof(SmemCtl) + kStagingBytes + 1024;
+  kp.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - staging - 1024 - res_bytes) / stage_bytes));
+  const size_t smem = static_cast<size_t>(res_bytes) + static_cast<size_t>(kp.stages) * stage_bytes + sizeof(SmemCtl) + staging + 1024;
   int grid;  // in scheduling slots: CTAs, or CTA pairs
   if (kp.b_resident) {
     const int groups = std::min(slots / kp.num_n_tiles, kp.num_m_tiles);
@@ -714,7 +788,7 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   if (kp.pair) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
@@ -724,7 +798,7 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
     cfg.numAttrs = 1;
     TT_CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, kp));
   } else {
-    fn<<<grid, kThreads, smem, s>>>(kp);
+    fn<<<grid, threads, smem, s>>>(kp);
   }
   prof_record(s, false, flops, 0, tag);
   TT_LAUNCH_CHECK();

@@ -459,6 +459,169 @@ __global__ void __launch_bounds__(384) k_dec_cross_attn(DecoderStep st, const __
   }
 }
 
+// Refinement pass: all L (<= 32) query positions of a crop at once, on mma.sync tensor cores (the per-position
+// kernels above re-read a crop's K/V once per position: 26 x 196 KB from L2 for the cross attention).
+// grid (3, crops), 4 warps: block = one 128-dim slice of the 384 (4 heads), warp = head (32 dims).  The slice's K
+// and V rows (KEYS x 256 B each) are staged with cp.async into padded smem (272-byte pitch: ldmatrix rows fall in
+// distinct banks); S = Q K^T and O = P V are m16n8k16 bf16 MMAs, softmax in registers on the accumulator layout.
+//   SELF = false: cross attention, q bf16 [crop*np + p][D], kv = memory K|V [crop][128][2D], no mask.
+//   SELF = true : self attention over the content cache, q fp32 table [p][D] shared by all crops,
+//                 kv = [crop][L][2D], cloze mask (key != p + 1) and key padding from the first EOS on.
+constexpr int kRefPitch = 136;  // bf16 elements per staged row (128 + 8 pad)
+template <int KEYS, bool SELF>
+__global__ void __launch_bounds__(128) k_dec_attn_refine(const void* __restrict__ q_in, const __nv_bfloat16* __restrict__ kv,
+                                                         int nkeys, int np, const int* __restrict__ tokens, int eos_id,
+                                                         int L, __nv_bfloat16* __restrict__ out) {
+  constexpr int kD = 384, kNT = KEYS / 8, kKS = KEYS / 16;
+  extern __shared__ __align__(16) uint8_t ref_smem[];
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(ref_smem);
+  __nv_bfloat16* sV = sK + KEYS * kRefPitch;
+  const int hg = blockIdx.x, crop = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* kvb = kv + static_cast<long long>(crop) * nkeys * 2 * kD + hg * 128;
+  // stage K then V: 16 chunks of 16 B per row
+  for (int pass = 0; pass < 2; ++pass) {
+    __nv_bfloat16* dst = pass ? sV : sK;
+    for (int c = threadIdx.x; c < KEYS * 16; c += 128) {
+      const int row = c >> 4, ch = c & 15;
+      const uint32_t d = ptx::smem_u32(dst + row * kRefPitch + ch * 8);
+      if (row < nkeys) {
+        const __nv_bfloat16* src = kvb + static_cast<long long>(row) * 2 * kD + pass * kD + ch * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+      } else {
+        ptx::sts128(d, make_uint4(0u, 0u, 0u, 0u));
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // Q fragments of this warp's head: A (row-major 16x16) x 2 m-tiles x 2 k-steps
+  const int dbase = hg * 128 + warp * 32;
+  uint32_t qa[2][2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int p = mt * 16 + (lane >> 2) + (i & 1) * 8;
+        const int col = dbase + ks * 16 + (lane & 3) * 2 + (i >> 1) * 8;
+        uint32_t v = 0u;
+        if (p < np) {
+          if constexpr (SELF) {
+            const float2 f = *reinterpret_cast<const float2*>(static_cast<const float*>(q_in) + p * kD + col);
+            __nv_bfloat162 h = __floats2bfloat162_rn(f.x, f.y);
+            v = *reinterpret_cast<uint32_t*>(&h);
+          } else {
+            v = *reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(q_in) +
+                                                   (static_cast<long long>(crop) * np + p) * kD + col);
+          }
+        }
+        qa[mt][ks][i] = v;
+      }
+  int first_eos = L;
+  if constexpr (SELF) {
+    const int t = (lane + 1 < L) ? tokens[crop * L + lane + 1] : -1;  // lane l holds token l+1
+    const unsigned m = __ballot_sync(0xffffffffu, t == eos_id);
+    if (m) first_eos = __ffs(m);
+  }
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+  __syncthreads();
+  float sc[2][kNT][4];
+#pragma unroll
+  for (int nt = 0; nt < kNT; ++nt) {
+    uint32_t b[4];
+    const uint32_t addr = ptx::smem_u32(sK + (nt * 8 + (lane & 7)) * kRefPitch + warp * 32 + (lane >> 3) * 8);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(addr));
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float* c = sc[mt][nt];
+      c[0] = c[1] = c[2] = c[3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                     : "r"(qa[mt][ks][0]), "r"(qa[mt][ks][1]), "r"(qa[mt][ks][2]), "r"(qa[mt][ks][3]), "r"(b[2 * ks]), "r"(b[2 * ks + 1]));
+    }
+  }
+  // masked softmax per query row; a row's 2*kNT values per thread, 4 threads per row
+  const float scale = 0.17677669529663687f;  // 1/sqrt(32)
+  float inv[2][2];
+  uint32_t pp[2][kNT][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int p = mt * 16 + (lane >> 2) + hf * 8;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = nt * 8 + (lane & 3) * 2 + e;
+          bool ok = key < nkeys;
+          if constexpr (SELF) ok = ok && key != p + 1 && key < first_eos;
+          float& v = sc[mt][nt][hf * 2 + e];
+          v = ok ? v * scale : -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < kNT; ++nt) {
+        const float e0 = __expf(sc[mt][nt][hf * 2] - mx), e1 = __expf(sc[mt][nt][hf * 2 + 1] - mx);
+        sum += e0 + e1;
+        __nv_bfloat162 h = __floats2bfloat162_rn(e0, e1);
+        pp[mt][nt][hf] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      inv[mt][hf] = 1.f / sum;
+    }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  float o[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int n4 = 0; n4 < 4; ++n4) o[mt][n4][0] = o[mt][n4][1] = o[mt][n4][2] = o[mt][n4][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < kKS; ++ks) {
+#pragma unroll
+    for (int dp = 0; dp < 2; ++dp) {  // two 16-dim halves of the head
+      uint32_t b[4];
+      const int mi = lane >> 3;
+      const uint32_t addr = ptx::smem_u32(sV + (ks * 16 + (mi & 1) * 8 + (lane & 7)) * kRefPitch + warp * 32 + dp * 16 + (mi >> 1) * 8);
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(addr));
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float* c = o[mt][dp * 2 + j];
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                       : "r"(pp[mt][2 * ks][0]), "r"(pp[mt][2 * ks][1]), "r"(pp[mt][2 * ks + 1][0]), "r"(pp[mt][2 * ks + 1][1]),
+                         "r"(b[2 * j]), "r"(b[2 * j + 1]));
+        }
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const int p = mt * 16 + (lane >> 2) + hf * 8;
+      if (p >= np) continue;
+      __nv_bfloat16* orow = out + (static_cast<long long>(crop) * np + p) * kD + dbase + (lane & 3) * 2;
+#pragma unroll
+      for (int n4 = 0; n4 < 4; ++n4) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(o[mt][n4][hf * 2] * inv[mt][hf], o[mt][n4][hf * 2 + 1] * inv[mt][hf]);
+        *reinterpret_cast<__nv_bfloat162*>(orow + n4 * 8) = h;
+      }
+    }
+}
+
 __global__ void k_argmax(const float* __restrict__ logits, int rows, int n_cls, int ld, int* __restrict__ ids,
                          int ids_stride, int* __restrict__ next, int next_stride, const int* __restrict__ forced,
                          int forced_stride) {
@@ -551,6 +714,12 @@ cudaError_t dec_self_attn(const DecoderStep& st, const float* q_table, const __n
                           int eos_id, __nv_bfloat16* out, cudaStream_t s) {
   if (st.n_crops <= 0) return cudaSuccess;
   if (st.D != st.heads * 32 || st.L > 32) { set_error("dec_self_attn: head dim must be 32, L <= 32"); return cudaErrorInvalidValue; }
+  if (st.refine && st.p0 == 0 && st.np == st.L && st.D == 384) {
+    constexpr int smem = 2 * 32 * kRefPitch * 2;
+    k_dec_attn_refine<32, true><<<dim3(3, st.n_crops), 128, smem, s>>>(q_table, kv, st.L, st.np, tokens, eos_id, st.L, out);
+    TT_LAUNCH_CHECK();
+    return cudaSuccess;
+  }
   k_dec_self_attn<<<dim3(st.np, st.n_crops), st.heads * 32, 0, s>>>(st, q_table, kv, tokens, eos_id, out);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
@@ -560,6 +729,13 @@ cudaError_t dec_cross_attn(const DecoderStep& st, const __nv_bfloat16* q, const 
                            __nv_bfloat16* out, cudaStream_t s) {
   if (st.n_crops <= 0) return cudaSuccess;
   if (st.D != 384 || st.heads != 12) { set_error("dec_cross_attn: built for D = 384, 12 heads"); return cudaErrorInvalidValue; }
+  if (st.np > 1 && st.np <= 32) {
+    constexpr int smem = 2 * 128 * kRefPitch * 2;
+    TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(k_dec_attn_refine<128, false>), smem));
+    k_dec_attn_refine<128, false><<<dim3(3, st.n_crops), 128, smem, s>>>(q, mem_kv, 128, st.np, nullptr, 0, st.L, out);
+    TT_LAUNCH_CHECK();
+    return cudaSuccess;
+  }
   k_dec_cross_attn<<<dim3(st.np, st.n_crops), 384, 0, s>>>(st, q, mem_kv, out);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
