@@ -339,6 +339,13 @@ def run_native(args, rank, local_rank, world):
             pm, pf, pl = C.c_double(), C.c_double(), C.c_ulonglong()
             lib.tt_profile_collect(C.byref(pm), C.byref(pf), C.byref(pl))
             prof = (pm.value, pf.value, pl.value)
+            buf = C.create_string_buffer(1 << 14)
+            lib.tt_profile_stages(buf, len(buf))
+            stages = {}
+            for ln in buf.value.decode().splitlines():
+                name, cnt, sms, sfl, sby = ln.split(",")
+                stages[name] = dict(ms=float(sms) / steps, flops=float(sfl) / steps, bytes=float(sby) / steps)
+            prof = prof + (stages,)
         w1 = datetime.now()
         h1, d1 = C.c_ulonglong(), C.c_ulonglong()
         lib.tt_io_bytes(C.byref(h1), C.byref(d1))
@@ -356,12 +363,41 @@ def run_native(args, rank, local_rank, world):
     r_prof = timed(step_dev, args.steps, profile=True)
     lib.tt_engine_set_slots(eng._h, 0)
 
+    peaks = measured_peaks()
+    # BASELINE.json's second metric: PARSeq crops/s on a batch of 1024 synthetic 32x128 crops (configs[2]),
+    # through tt_parseq_forward with host buffers in and ids out
+    crops = np.random.default_rng(0).integers(0, 256, (1024, 32, 128, 3), dtype=np.uint8)
+    ids = np.empty((1024, 26), dtype=np.int32)
+    def pq():
+        tb.check(lib.tt_parseq_forward(eng._h, crops.ctypes.data, 1024, None, None, ids.ctypes.data), "tt_parseq_forward")
+    pq()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        pq()
+    torch.cuda.synchronize()
+    parseq_cps = 5 * 1024 / (time.perf_counter() - t0)
+
     sampler.stop()
     clocks = sampler.window(*r_dev["window"])
     value = job_throughput(n, world, args.steps, r_dev["ms"])
     e2e = job_throughput(n, world, args.steps, r_host["ms"])
-    peaks = measured_peaks()
-    pm, pf, pl = r_prof["prof"]
+    pm, pf, pl, stages = r_prof["prof"]
+    # per-stage rooflines (north_star: "each stage reported as a fraction of its roofline"): algorithmic FLOPs or
+    # bytes of the stage / its CUDA-event time in the serial pass, against the measured peaks
+    stage_lines = {}
+    for name, st in stages.items():
+        sec = st["ms"] / 1e3
+        if sec <= 0:
+            continue
+        tf, gbs = st["flops"] / sec / 1e12, st["bytes"] / sec / 1e9
+        bound = "tensor" if name in ("craft", "parseq_encoder") else "hbm"
+        ent = {"ms_per_step": st["ms"], "share_of_serial_step": st["ms"] / (r_prof["ms"] / args.steps), "bound": bound}
+        if st["flops"] > 0:
+            ent.update(tflops=tf, frac_tensor=tf / peaks["tf_sustained"])
+        if st["bytes"] > 0:
+            ent.update(gbs=gbs, frac_hbm=gbs / peaks["hbm"])
+        stage_lines[name] = ent
     achieved = pf / (pm / 1e3) / 1e12 if pm > 0 else 0.0
     line = {
         "metric": "pages/sec end-to-end", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
@@ -384,6 +420,10 @@ def run_native(args, rank, local_rank, world):
                      "note": "per-launch events from an extra timed pass with one execution slot (serial kernels); "
                              "the headline value runs two slots per GPU",
                      "algorithmic_gflop_per_step": n * (CRAFT_GFLOP_PER_PAGE + WORDS * PARSEQ_GFLOP_PER_CROP)},
+        "stages": stage_lines,
+        "parseq": {"crops_per_s": parseq_cps, "batch": 1024, "frac_tensor": parseq_cps * PARSEQ_GFLOP_PER_CROP / 1e3 / peaks["tf_sustained"],
+                   "note": "configs[2]: 1024 synthetic 32x128 crops, PARSeq-base, 26 AR steps + refinement, host u8 crops in / ids out "
+                           "(wall clock around tt_parseq_forward, this rank)"},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, npg, threads = cpu_pipeline_sample(1)

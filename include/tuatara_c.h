@@ -46,7 +46,7 @@ typedef struct tt_config {
   float low_text;       /* 0.4   tuatara.cpp:399 */
   int min_area;         /* 10    tuatara.cpp:148 */
   int max_batch_pages;  /* pages processed per CRAFT batch per GPU (0 = default 8) */
-  int slots_per_gpu;    /* concurrent execution slots (streams + host threads) per GPU: 0 = default 2, max 2 */
+  int slots_per_gpu;    /* concurrent execution slots (streams + host threads) per GPU: 0 = default 2, max 4 */
 } tt_config;
 
 typedef struct tt_item {
@@ -103,6 +103,12 @@ TT_API void tt_profile_enable(int on);
 TT_API void tt_profile_collect(double* total_ms, double* total_flops, unsigned long long* launches);
 /* Same, and appends one CSV line per launch ("tag,flops,ms") to `path` (per-layer tables in profiles/). */
 TT_API void tt_profile_dump(const char* path, double* total_ms, double* total_flops, unsigned long long* launches);
+
+/* Stage-level timings recorded while the profile is enabled: "name,count,ms,flops,bytes\n" per stage of
+ * image_to_data (preprocess tuatara.cpp:206-234, craft :376, postprocess :119-204, crop_resize :416-448,
+ * parseq_encoder / parseq_decoder :307), flops / bytes being the stage's algorithmic work.  Writes at most
+ * cap-1 characters + NUL, returns the full length, clears the log. */
+TT_API int tt_profile_stages(char* buf, int cap);
 
 /* ---------------------------------------------------- stage level, host memory */
 /* Size arithmetic of resize_aspect_ratio (tuatara.cpp:211-226), fp32 like the reference. */

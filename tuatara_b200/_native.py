@@ -67,6 +67,7 @@ SIGNATURES = {
     "tt_profile_enable": (None, [_I]),
     "tt_profile_collect": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "tt_profile_dump": (None, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
+    "tt_profile_stages": (_I, [C.c_char_p, _I]),
     "tt_resize_plan": (_I, [_I, _I, _F, _F, _PI, _PI, _PI, _PI, _PF]),
     "tt_preprocess": (_I, [C.POINTER(tt_image), _F, _F, _P]),
     "tt_craft_forward": (_I, [_P, _P, _I, _I, _P]),

@@ -58,6 +58,56 @@ void prof_collect(double* total_ms, double* total_flops, double* total_bytes, un
   g_prof.clear();
 }
 
+namespace {
+std::vector<ProfRec> g_stage;
+thread_local cudaEvent_t t_stage_open = nullptr;
+}  // namespace
+
+void stage_begin(cudaStream_t s) {
+  if (!prof_enabled()) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, s);
+  t_stage_open = ev;
+}
+
+void stage_end(cudaStream_t s, const char* name, double flops, double bytes) {
+  if (!prof_enabled() || t_stage_open == nullptr) return;
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, s);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_stage.push_back(ProfRec{t_stage_open, ev, flops, bytes, name});
+  t_stage_open = nullptr;
+}
+
+std::string stage_collect() {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  struct Agg { int n = 0; double ms = 0, fl = 0, by = 0; };
+  std::vector<std::pair<std::string, Agg>> agg;
+  for (ProfRec& r : g_stage) {
+    cudaEventSynchronize(r.b);
+    float t = 0.f;
+    const bool ok = cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+    if (!ok) continue;
+    auto it = agg.begin();
+    for (; it != agg.end(); ++it)
+      if (it->first == r.tag) break;
+    if (it == agg.end()) { agg.emplace_back(r.tag, Agg{}); it = agg.end() - 1; }
+    it->second.n += 1; it->second.ms += t; it->second.fl += r.flops; it->second.by += r.bytes;
+  }
+  g_stage.clear();
+  std::string out;
+  char line[256];
+  for (auto& kv : agg) {
+    std::snprintf(line, sizeof(line), "%s,%d,%.6f,%.0f,%.0f\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.fl, kv.second.by);
+    out += line;
+  }
+  return out;
+}
+
 cudaError_t ensure_dynamic_smem(const void* func, int bytes) {
   static std::mutex mu;
   static std::map<std::pair<const void*, int>, cudaError_t> done;

@@ -22,6 +22,12 @@ void prof_record(cudaStream_t s, bool begin, double flops, double bytes, const c
 // dump_path != nullptr: also append one CSV line per launch (tag, flops, ms) to that file.
 void prof_collect(double* total_ms, double* total_flops, double* total_bytes, unsigned long long* launches,
                   const char* dump_path = nullptr);
+// Stage-level timing for bench.py's per-stage rooflines (same switch as the per-launch profile): a stage is a run
+// of kernels on one stream bracketed by two events; flops / bytes are the stage's ALGORITHMIC work.
+void stage_begin(cudaStream_t s);
+void stage_end(cudaStream_t s, const char* name, double flops, double bytes);
+// "name,count,ms,flops,bytes\n" per stage (summed over the recorded intervals); clears the log.
+std::string stage_collect();
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: set it once per (kernel, device).
 cudaError_t ensure_dynamic_smem(const void* func, int bytes);
 

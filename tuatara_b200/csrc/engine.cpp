@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -97,6 +98,7 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
   if (!pages_dev || !craft_in) { set_error("arena exhausted (pages)"); return 1; }
   const size_t page_stride = (page_bytes + 255) & ~size_t(255);
   std::vector<PageRef> refs(B);
+  stage_begin(d.stream);
   for (int b = 0; b < B; ++b) {
     const tt_image& im = pages[idx[b]];
     uint8_t* dst = pages_dev + b * page_stride;
@@ -111,8 +113,12 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
     E_TRY(page_resize_pad(refs[b].data, im.rows, im.cols, refs[b].step, craft_in + b * in_bytes, th, tw, h32, w32,
                           d.stream));
   }
+  stage_end(d.stream, "preprocess", 0.0, static_cast<double>(B) * (page_bytes + in_bytes));
   float* maps = nullptr;
+  stage_begin(d.stream);
   E_TRY(d.craft_forward(craft_in, B, h32, w32, &maps));
+  // 27 convolutions of CRAFT: 711.4 FLOP per input pixel (= 746.0 GFLOP at 1024 x 1024)
+  stage_end(d.stream, "craft", 746.0e9 / (1024.0 * 1024.0) * B * h32 * w32, 0.0);
   if (opt.score_override) {
     const size_t map_elems = static_cast<size_t>(h32 / 2) * (w32 / 2) * 2;
     for (int b = 0; b < B; ++b)
@@ -124,7 +130,9 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
       }
   }
   std::vector<std::vector<DetBox>> det;
+  stage_begin(d.stream);
   if (detect_boxes(d, cfg, maps, B, h32 / 2, w32 / 2, &det)) return 1;
+  stage_end(d.stream, "postprocess", 0.0, 24.0 * B * (h32 / 2) * (w32 / 2));  // 24 B per map pixel
 
   // host: rescale boxes, bounding rects, output bboxes (tuatara.cpp:406-418, :256-274)
   const float inv = 1.f / ratio;  // ratio_w == ratio_h (tuatara.cpp:360-361)
@@ -182,7 +190,13 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
     E_CUDA(cudaMemcpyAsync(boxes_dev, crops.data() + c0, sizeof(CropBox) * nc, cudaMemcpyHostToDevice, d.stream));
     g_h2d_bytes += sizeof(PageRef) * B + sizeof(CropBox) * nc + sizeof(int) * nc * d.w->pd.L /*token init*/;
     g_d2h_bytes += sizeof(int) * nc * d.w->pd.L;
+    stage_begin(d.stream);
     E_TRY(crop_resize(refs_dev, boxes_dev, nc, nullptr, patches, d.stream));
+    {
+      double src = 0;
+      for (int c = c0; c < c0 + nc; ++c) src += 3.0 * crops[c].w * crops[c].h;
+      stage_end(d.stream, "crop_resize", 0.0, src + static_cast<double>(nc) * 128 * 96 * 2);  // source rect + bf16 patch rows
+    }
     float* logits = nullptr;
     int* ids = nullptr;
     E_TRY(d.parseq_forward(patches, nc, nullptr, &logits, &ids));
@@ -219,7 +233,9 @@ int run_device(tt_engine& e, int g, const tt_image* pages, const std::vector<int
     groups.push_back(std::move(grp));
     i = j;
   }
-  const int want = cfg.slots_per_gpu > 0 ? std::min(cfg.slots_per_gpu, kSlotsPerDevice) : kSlotsPerDevice;
+  static const int env_slots = std::getenv("TT_SLOTS") ? std::atoi(std::getenv("TT_SLOTS")) : 0;  // development override
+  const int dflt = env_slots > 0 ? env_slots : 2;
+  const int want = std::min(cfg.slots_per_gpu > 0 ? cfg.slots_per_gpu : dflt, kSlotsPerDevice);
   const int S = std::min<int>(want, static_cast<int>(groups.size()));
   std::vector<int> rcs(S, 0);
   std::vector<std::string> errs(S);
@@ -294,6 +310,14 @@ void tt_io_bytes(unsigned long long* h2d, unsigned long long* d2h) {
 void tt_profile_enable(int on) { prof_enable(on != 0); }
 void tt_profile_collect(double* total_ms, double* total_flops, unsigned long long* launches) {
   prof_collect(total_ms, total_flops, nullptr, launches);
+}
+int tt_profile_stages(char* buf, int cap) {
+  const std::string csv = stage_collect();
+  if (!buf || cap <= 0) return static_cast<int>(csv.size());
+  const size_t n = std::min(csv.size(), static_cast<size_t>(cap - 1));
+  std::memcpy(buf, csv.data(), n);
+  buf[n] = 0;
+  return static_cast<int>(csv.size());
 }
 void tt_profile_dump(const char* path, double* total_ms, double* total_flops, unsigned long long* launches) {
   prof_collect(total_ms, total_flops, nullptr, launches, path);

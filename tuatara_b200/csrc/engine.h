@@ -71,7 +71,7 @@ struct DeviceWeights {
 // One execution slot: a stream with its own scratch arena and workspaces.  Each GPU runs kSlotsPerDevice
 // of them from separate host threads so that one slot's host-side phases (box geometry, result
 // assembly, D2H waits) are covered by the other slot's kernels.
-constexpr int kSlotsPerDevice = 2;
+constexpr int kSlotsPerDevice = 4;   // upper bound; tt_config.slots_per_gpu picks how many run (default 2)
 
 struct DeviceCtx {
   int device = 0;

@@ -722,20 +722,25 @@ int max_pairs(const void* fn, size_t smem, int threads) {
   return cached;
 }
 
-// Epilogue warps per CTA: 16 for the bf16-output kernels (their epilogue instruction stream set the pace with 8),
-// 8 for the fp32 / residual ones (HBM-bound) and the CRAFT head.  TT_GEMM_EW=8 forces 8 everywhere (development).
-int epi_warps(const Epilogue& e) {
+// Epilogue warps per CTA.  Measured (tools/gpu_dbg.sh, profiles/r1b_gemm_roles.md): 16 warps only pay for the GELU
+// epilogue on 256-wide tiles (MUFU-bound, +5 %); elsewhere the epilogue is bound by shared per-SM resources (TMEM
+// read port, store path), 16 warps cost a smem stage and split 192/64-wide tiles into half-filled 64-byte segments.
+// TT_GEMM_EW=8|16 forces one value (development).
+int epi_warps(const Epilogue& e, int BN) {
   static const int ew_env = env_int("TT_GEMM_EW", 0);
-  if (ew_env == 8) return 8;
-  return e.out_type == OUT_BF16 ? 16 : 8;
+  if (e.out_type == OUT_CLS_TAIL) return 8;
+  if (ew_env == 8 || ew_env == 16) return ew_env;
+  return (e.out_type == OUT_BF16 && e.act == ACT_GELU && BN % 128 == 0) ? 16 : 8;
 }
 
 template <bool PAIR>
-void (*select_kernel(const Epilogue& e))(const KParams) {
+void (*select_kernel(const Epilogue& e, int ew))(const KParams) {
   if (e.out_type == OUT_CLS_TAIL) return gemm_tc_kernel<OUT_CLS_TAIL, ACT_RELU, false, PAIR, 8>;
+  if (e.out_type == OUT_F32 && ew == 16)
+    return e.res_type == RES_F32 ? gemm_tc_kernel<OUT_F32, ACT_NONE, true, PAIR, 16> : gemm_tc_kernel<OUT_F32, ACT_NONE, false, PAIR, 16>;
   if (e.out_type == OUT_F32)
     return e.res_type == RES_F32 ? gemm_tc_kernel<OUT_F32, ACT_NONE, true, PAIR, 8> : gemm_tc_kernel<OUT_F32, ACT_NONE, false, PAIR, 8>;
-  if (epi_warps(e) == 8) {
+  if (ew == 8) {
     if (e.act == ACT_RELU) return gemm_tc_kernel<OUT_BF16, ACT_RELU, false, PAIR, 8>;
     if (e.act == ACT_GELU) return gemm_tc_kernel<OUT_BF16, ACT_GELU, false, PAIR, 8>;
     return gemm_tc_kernel<OUT_BF16, ACT_NONE, false, PAIR, 8>;
@@ -755,10 +760,11 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   const int b_rows = kp.pair ? kp.BN / 2 : kp.BN;
   const int a_bytes = kBlockM * row_bytes, b_bytes = b_rows * row_bytes;
   using KernelFn = void (*)(const KParams);
-  const KernelFn fn = kp.pair ? select_kernel<true>(kp.epi) : select_kernel<false>(kp.epi);
+  const int ew = epi_warps(kp.epi, kp.BN);
+  const KernelFn fn = kp.pair ? select_kernel<true>(kp.epi, ew) : select_kernel<false>(kp.epi, ew);
   TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
-  const int threads = 64 + 32 * epi_warps(kp.epi);
-  const int staging = epi_warps(kp.epi) * 2048;
+  const int threads = 64 + 32 * ew;
+  const int staging = ew * 2048;
   const int slots = kp.pair ? max_pairs(reinterpret_cast<const void*>(fn), 200 * 1024, threads) : num_sms();
   if (kp.b_resident && (num_kb * b_bytes > (kp.pair ? kResidentMaxPair : kResidentMax) || kp.num_n_tiles > slots)) kp.b_resident = 0;
   const int res_bytes = kp.b_resident ? num_kb * b_bytes : 0;

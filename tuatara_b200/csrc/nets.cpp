@@ -263,6 +263,7 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
   ARENA_GET(mem, bf, Mc * D);
   ARENA_GET(mem_kv, bf, static_cast<size_t>(M) * 2 * D);
 
+  stage_begin(s);
   for (int c0 = 0; c0 < n; c0 += chunk) {
     const int nc = std::min(chunk, n - c0);
     const int Mi = nc * 128;
@@ -285,6 +286,7 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
             nullptr, RES_NONE, 0, 0, mem_kv + static_cast<size_t>(c0) * 128 * 2 * D, OUT_BF16, 2 * D));
   }
 
+  stage_end(s, "parseq_encoder", 5.75e9 * n, 0.0);  // 2 x 2.874 GMAC per crop
   // ---- decoder: 26 autoregressive steps + one cloze refinement
   const int R = n * L;
   ARENA_GET(kv_cache, bf, static_cast<size_t>(R) * 2 * D);
@@ -305,6 +307,7 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
     TT_CUDA_TRY(cudaStreamSynchronize(s));  // `init` is stack-owned
   }
   const float* posq = wf.f32("posq");
+  stage_begin(s);
   auto stream_tail = [&](const DecoderStep& st, int rows, float* logits_dst, int ldl) -> cudaError_t {
     // t = posq[p] + out_proj(self_attn); t += cross_attn(norm1(t)); t += mlp(norm2(t)); head(norm(t))
     RUN(dec_self_attn(st, w->q_sa_table, kv_cache, tokens, pd.eos_id, ab, s));
@@ -335,6 +338,8 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
   DecoderStep st{n, D, pd.dec_heads, L, 0, L, 1};
   RUN(stream_tail(st, R, logits, NC));
   RUN(argmax_rows(logits, R, pd.n_cls, NC, ids, 1, nullptr, 0, nullptr, 0, s));
+  // decoder: 2 x 0.153 GMAC per crop; its floor is the 27 reads of the crop's memory K|V (128 x 768 bf16)
+  stage_end(s, "parseq_decoder", 0.306e9 * n, 27.0 * n * 128 * 768 * 2);
   *logits_out = logits;
   *ids_out = ids;
   return cudaSuccess;
