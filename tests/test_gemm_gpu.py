@@ -148,3 +148,21 @@ def _conv(native_lib, B, H, W, C0, C1, Cout, taps, dil, relu=1, BN=0, seed=0, re
 def test_conv_shapes(native_lib, B, H, W, C0, C1, Cout, taps, dil):
     out, ref = _conv(native_lib, B, H, W, C0, C1, Cout, taps, dil)
     _check(out.reshape(-1, Cout), ref.reshape(-1, Cout), taps * (C0 + C1), f"conv {B}x{H}x{W} C{C0}+{C1}->{Cout} t{taps} d{dil}")
+
+
+@pytest.mark.parametrize("M,K,N", [(2400, 384, 384), (307200 // 8, 1536, 384), (1000, 96, 384), (129, 384, 128)])
+def test_linear_residual_in_place(native_lib, M, K, N):
+    """x += A W^T + b with out == residual (the PARSeq residual stream; TMA epilogue: residual chunks are loaded,
+    updated in place in smem and stored back to the same addresses)."""
+    from tuatara_b200._native import check
+
+    g = torch.Generator(device="cpu").manual_seed(3)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.1).to(torch.bfloat16).cuda()
+    b = torch.randn(N, generator=g).float().cuda()
+    x = torch.randn(M, N, generator=g).float().cuda()
+    ref = (A.float() @ W.float().t() + b + x).cpu()
+    check(native_lib.tt_linear_dev(A.data_ptr(), K, M, K, W.data_ptr(), N, b.data_ptr(), 0, x.data_ptr(), 1, N,
+                                   x.data_ptr(), 1, N, 0, 0, None), "tt_linear_dev")
+    torch.cuda.synchronize()
+    _check(x.cpu(), ref, K, f"in-place residual linear M{M} K{K} N{N}")

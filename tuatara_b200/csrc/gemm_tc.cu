@@ -44,10 +44,15 @@ constexpr int kSmemBudget = 227 * 1024;
 constexpr int kResidentMax = 64 * 1024;   // largest weight slice kept resident in smem (leaves >= 8 A stages)
 constexpr int kResidentMaxPair = 100 * 1024;  // PAIR: half of a 256 x 384 slice (96 KB) + 6 A stages
 constexpr int kStagingBytes = kMaxEpiWarps * 2048;  // epilogue transpose tiles, 2 KB per warp (upper bound, used for planning)
+// TMA epilogue (fp32 residual GEMMs): ring of [128 rows x 32 fp32] SWIZZLE_128B chunks that the residual is loaded
+// into, updated in place by the epilogue warps and stored from
+constexpr int kResSlots = 4;
+constexpr int kResSlotBytes = 128 * 128;
 
 struct KParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
+  CUtensorMap tmR, tmC;  // TMA epilogue: fp32 residual (load) and output (store), box {32 cols, 128 rows}
   int mode;  // 0 plain rows, 1 conv tiles
   int M, N, BN, BK;
   int kb_src[2];
@@ -69,6 +74,7 @@ struct alignas(16) SmemCtl {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint64_t b_full;
+  uint64_t res_full[kResSlots], res_empty[kResSlots], chunk_done[kResSlots];  // TMA epilogue ring
   uint32_t tmem_base;
   float tail[16 * 16 + 16 + 2 * 16 + 2];
   alignas(16) float bias[2][256];  // the tile's bias row, staged per accumulator stage (broadcast reads in the epilogue)
@@ -130,6 +136,7 @@ __device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
   return r;
 }
+__device__ __forceinline__ void upk2u(uint64_t v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
 __device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t d;
@@ -169,9 +176,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // OUT: OUT_BF16 / OUT_F32 / OUT_CLS_TAIL; ACT: ACT_*; RES: fp32 residual added (OUT_F32 only).  The epilogue is
 // specialised at compile time: with these as runtime flags only ~1/4 of its executed instructions were
 // useful work (ncu opcode histogram, profiles/r1_gemm_epilogue.md) and it, not the MMA, set the pace.
-template <int OUT, int ACT, bool RES, bool PAIR, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_constant__ KParams p) {
-  constexpr int kThreads = 64 + 32 * EW;
+// TE ("TMA epilogue", fp32 output + fp32 residual only): warp 2 streams the residual tile through a smem ring with
+// TMA loads that run ahead of the MMAs (the register path had one 2 KB segment per warp in flight and the
+// epilogue took 2.6x the mainloop: profiles/r1b_gemm_roles.md), 4 epilogue warps add accumulator + bias to their
+// own rows in place, warp 3 writes the chunk back with a TMA store.  No per-thread global access at all.
+template <int OUT, int ACT, bool RES, bool PAIR, int EW, bool TE = false>
+__global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kernel(const __grid_constant__ KParams p) {
+  static_assert(!TE || (OUT == OUT_F32 && RES && EW == 4), "TMA epilogue: fp32 out + residual, 4 epilogue warps");
+  constexpr int kThreads = 64 + 32 * EW + (TE ? 64 : 0);
+  constexpr int kEpiWarp0 = TE ? 4 : 2;   // first epilogue warp (a multiple of 4 apart from 2: TMEM quadrant = warp & 3)
   constexpr int kEpiWarps = EW;
   constexpr int kParts = EW / 4;   // warps sharing a TMEM lane quadrant split the tile's columns
   extern __shared__ uint8_t smem_raw[];
@@ -187,7 +200,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
   const int stage_bytes = resident ? a_bytes : a_bytes + b_bytes;
   uint8_t* sBres = smem;                                        // [num_kb][BN rows] when resident
   uint8_t* ring = smem + (resident ? num_kb * b_bytes : 0);
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(ring + p.stages * stage_bytes);
+  uint8_t* res_ring = ring + p.stages * stage_bytes;            // TE only
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(res_ring + (TE ? kResSlots * kResSlotBytes : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -205,6 +219,15 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
       ptx::mbar_init(&ctl->acc_empty[s], PAIR ? 2 * kEpiWarps : kEpiWarps);  // PAIR: both CTAs' epilogues free the leader's
     }
     ptx::mbar_init(&ctl->b_full, 1);
+    if constexpr (TE) {
+      ptx::prefetch_tmap(&p.tmR);
+      ptx::prefetch_tmap(&p.tmC);
+      for (int s = 0; s < kResSlots; ++s) {
+        ptx::mbar_init(&ctl->res_full[s], 1);
+        ptx::mbar_init(&ctl->res_empty[s], 1);
+        ptx::mbar_init(&ctl->chunk_done[s], 32 * EW);
+      }
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -329,7 +352,47 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
       }
       if ((p.debug & 4) && blockIdx.x == 0) { p.dbg_out[2] = dbg_w_acc; p.dbg_out[3] = dbg_w_full; p.dbg_out[4] = clock64() - dbg_t_start; }
     }
-  } else {
+  } else if (TE && warp == 2) {
+    // ------------------------------------------------- residual loader (TMA epilogue)
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t ph = 0;
+      for (TileIter it(p); it.valid(); it.next()) {
+        const int m_tile = PAIR ? it.m_tile(p) * 2 + static_cast<int>(rank) : it.m_tile(p);
+        const int n0 = it.n_tile(p) * p.BN, m0 = m_tile * kBlockM;
+        const int rrow = p.epi.res_mod > 0 ? m0 % p.epi.res_mod : m0;
+        for (int c = 0; c < p.BN / 32; ++c) {
+          ptx::mbar_wait(&ctl->res_empty[slot], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&ctl->res_full[slot], kResSlotBytes);
+          // a pair's second tile may not exist, columns may end before the tile does: out-of-bounds parts arrive as zeros
+          ptx::tma_load_2d(res_ring + slot * kResSlotBytes, &p.tmR, &ctl->res_full[slot], n0 + c * 32, rrow);
+          if (++slot == kResSlots) { slot = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (TE && warp == 3) {
+    // --------------------------------------------------- output storer (TMA epilogue)
+    if (lane == 0) {
+      int slot = 0, prev = -1;
+      uint32_t ph = 0;
+      for (TileIter it(p); it.valid(); it.next()) {
+        const int m_tile = PAIR ? it.m_tile(p) * 2 + static_cast<int>(rank) : it.m_tile(p);
+        const int n0 = it.n_tile(p) * p.BN, m0 = m_tile * kBlockM;
+        for (int c = 0; c < p.BN / 32; ++c) {
+          ptx::mbar_wait(&ctl->chunk_done[slot], ph);
+          if ((p.debug & 3) == 0) ptx::tma_store_2d(&p.tmC, res_ring + slot * kResSlotBytes, n0 + c * 32, m0);  // rows/cols past the tensor are clipped
+          ptx::bulk_commit();
+          if (prev >= 0) {
+            ptx::bulk_wait_read<1>();             // the previous chunk's store has finished reading its slot
+            ptx::mbar_arrive(&ctl->res_empty[prev]);
+          }
+          prev = slot;
+          if (++slot == kResSlots) { slot = 0; ph ^= 1; }
+        }
+      }
+      ptx::bulk_wait<0>();
+    }
+  } else if (warp >= kEpiWarp0) {
     // ----------------------------------------------------------------- epilogue
     // Thread t of a warp owns accumulator row (TMEM lane) q*32 + t, but a row-per-thread global store
     // touches 32 different cache lines per instruction (measured: it halved the kernel's throughput).
@@ -340,9 +403,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
     constexpr int kEsize = kF32 ? 4 : 2;
     constexpr int kSegChunks = kF32 ? 1 : 2;     // 16-column chunks per 64-byte output segment
     const int q = warp & 3;                      // TMEM lane quadrant this warp may read
-    const int part = (warp - 2) >> 2;            // kParts warps share a quadrant and split the tile's columns
+    const int part = (warp - kEpiWarp0) >> 2;    // kParts warps share a quadrant and split the tile's columns
     const int r = q * 32 + lane;                 // tile row == TMEM lane
-    const uint32_t stg = ptx::smem_u32(reinterpret_cast<uint8_t*>(ctl + 1)) + (warp - 2) * 2048;
+    const uint32_t stg = ptx::smem_u32(reinterpret_cast<uint8_t*>(ctl + 1)) + (warp - kEpiWarp0) * 2048;
     const uint32_t bias_s = ptx::smem_u32(&ctl->bias[0][0]);
     const uint32_t own_row = stg + lane * 64;
     const int own_sw = (lane >> 1) & 3;          // swizzle of this thread's own row
@@ -383,25 +446,68 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
     };
     // bias of a tile's columns -> smem (a per-chunk LDG of it was 44% of all stall samples); the value for the
     // NEXT tile is fetched while this one is processed (its LDG latency was 9% of the samples after that).
-    const int bias_t = threadIdx.x - 64;  // 0 .. 32*EW-1 over the epilogue warps
-    auto bias_fetch = [&](const TileIter& t) -> float {
-      const int col0 = t.n_tile(p) * BN + bias_t, col1 = col0 + 32 * EW;
-      (void)col1;
-      return (t.valid() && bias_g != nullptr && bias_t < BN && col0 < N) ? __ldg(bias_g + col0) : 0.f;
+    const int bias_t = threadIdx.x - 32 * kEpiWarp0;  // 0 .. 32*EW-1 over the epilogue warps
+    constexpr int kBiasPer = (256 + 32 * EW - 1) / (32 * EW);  // bias columns per epilogue thread (BN <= 256)
+    auto bias_fetch = [&](const TileIter& t, float (&b)[kBiasPer]) {
+#pragma unroll
+      for (int i = 0; i < kBiasPer; ++i) {
+        const int tc = bias_t + i * 32 * EW, col = t.n_tile(p) * BN + tc;
+        b[i] = (t.valid() && bias_g != nullptr && tc < BN && col < N) ? __ldg(bias_g + col) : 0.f;
+      }
     };
     TileIter it(p);
-    float bias_cur = bias_fetch(it);
+    float bias_cur[kBiasPer];
+    bias_fetch(it, bias_cur);
+    int te_slot = 0;
+    uint32_t te_ph = 0;
+    (void)te_slot; (void)te_ph;
     for (; it.valid(); it.next()) {
       const int n_tile = it.n_tile(p), m_tile = PAIR ? it.m_tile(p) * 2 + static_cast<int>(rank) : it.m_tile(p);
       const int n0 = n_tile * BN;
       {
-        if (bias_t < BN) ptx::sts32(bias_s + (as * 256 + bias_t) * 4, __float_as_uint(bias_cur));
+#pragma unroll
+        for (int i = 0; i < kBiasPer; ++i)
+          if (bias_t + i * 32 * EW < BN) ptx::sts32(bias_s + (as * 256 + bias_t + i * 32 * EW) * 4, __float_as_uint(bias_cur[i]));
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");  // epilogue warps only
         TileIter nx = it;
         nx.next();
-        bias_cur = bias_fetch(nx);
+        bias_fetch(nx, bias_cur);
       }
-      if constexpr (OUT == OUT_CLS_TAIL) {
+      if constexpr (TE) {
+        // out = residual + (acc + bias), chunk by chunk: this thread's row of the chunk sits at r*128 in the slot,
+        // its 16-byte units XOR-swizzled by (r & 7) (SWIZZLE_128B) -- the same layout the TMA store reads back.
+        { const long long t0 = clock64(); ptx::mbar_wait(&ctl->acc_full[as], aphase); dbg_e_wait += clock64() - t0; }
+        const long long dbg_t_busy0 = clock64();
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+        const uint32_t bias_row = bias_s + as * 1024;
+        const uint32_t ring_s = ptx::smem_u32(res_ring);
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t raw[32];
+          ptx::tmem_ld<32>(t_row + c * 32, raw);
+          ptx::mbar_wait(&ctl->res_full[te_slot], te_ph);
+          ptx::tmem_ld_wait(raw);
+          const uint32_t rowaddr = ring_s + te_slot * kResSlotBytes + r * 128;
+          if (dbg != 2) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t a = rowaddr + ((k ^ (r & 7)) << 4);
+              const uint4 u = ptx::lds128(a);
+              const uint4 b = ptx::lds128(bias_row + (c * 32 + 4 * k) * 4);
+              const uint64_t v0 = add2(add2(pk2u(raw[4 * k + 0], raw[4 * k + 1]), pk2u(b.x, b.y)), pk2u(u.x, u.y));
+              const uint64_t v1 = add2(add2(pk2u(raw[4 * k + 2], raw[4 * k + 3]), pk2u(b.z, b.w)), pk2u(u.z, u.w));
+              uint4 o;
+              upk2u(v0, o.x, o.y);
+              upk2u(v1, o.z, o.w);
+              ptx::sts128(a, o);
+            }
+          }
+          ptx::fence_proxy_async();
+          ptx::mbar_arrive(&ctl->chunk_done[te_slot]);
+          if (++te_slot == kResSlots) { te_slot = 0; te_ph ^= 1; }
+        }
+        dbg_e_busy += clock64() - dbg_t_busy0;
+      } else if constexpr (OUT == OUT_CLS_TAIL) {
         // BN == 16: v = relu(conv 32->16 + b); two 1x1 convs in registers; fp32 [pixel][2] store
         long long orow;
         const bool valid = row_to_out(m_tile, r, orow);
@@ -572,8 +678,9 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tc_kernel(const __grid_c
       ++dbg_tiles;
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if ((p.debug & 4) && blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6)) {
-      p.dbg_out[5 + (warp == 6) * 3] = dbg_e_wait; p.dbg_out[6 + (warp == 6) * 3] = dbg_e_busy; p.dbg_out[7 + (warp == 6) * 3] = dbg_tiles;
+    if ((p.debug & 4) && blockIdx.x == 0 && lane == 0 && (warp == kEpiWarp0 || warp == kEpiWarp0 + 4)) {
+      const int o = (warp == kEpiWarp0 + 4) * 3;
+      p.dbg_out[5 + o] = dbg_e_wait; p.dbg_out[6 + o] = dbg_e_busy; p.dbg_out[7 + o] = dbg_tiles;
     }
   }
 
@@ -750,6 +857,31 @@ void (*select_kernel(const Epilogue& e, int ew))(const KParams) {
   return gemm_tc_kernel<OUT_BF16, ACT_NONE, false, PAIR, 16>;
 }
 
+// fp32 [rows][cols] tensor (row pitch ld elements) as a TMA map with a {32 cols, 128 rows} SWIZZLE_128B box
+bool make_tmap_f32_chunk(CUtensorMap* m, const void* base, long long rows, int cols, long long ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)"); return false; }
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fp32 chunk) failed with CUresult " + std::to_string(static_cast<int>(r))); return false; }
+  return true;
+}
+
+// The TMA epilogue handles plain row-major fp32 out = residual + acc + bias whose residual rows are the output rows
+// (or a table whose period is a multiple of the 128-row tile: the patch embedding's pos_embed).
+bool tma_epilogue_ok(const KParams& kp) {
+  static const int te_env = env_int("TT_GEMM_TE", 1);
+  const Epilogue& e = kp.epi;
+  return te_env != 0 && kp.mode == 0 && e.out_type == OUT_F32 && e.res_type == RES_F32 && e.act == ACT_NONE && kp.BN % 32 == 0 &&
+         kp.N % 4 == 0 && e.ldc % 4 == 0 && e.ldr % 4 == 0 && (e.res_mod == 0 || e.res_mod % kBlockM == 0) &&
+         reinterpret_cast<uintptr_t>(e.out) % 16 == 0 && reinterpret_cast<uintptr_t>(e.residual) % 16 == 0;
+}
+
 // kp.num_m_tiles holds the 128-row tile count on entry; PAIR mode turns it into the pair count.
 cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   const int row_bytes = kp.BK * 2;
@@ -760,11 +892,20 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   const int b_rows = kp.pair ? kp.BN / 2 : kp.BN;
   const int a_bytes = kBlockM * row_bytes, b_bytes = b_rows * row_bytes;
   using KernelFn = void (*)(const KParams);
-  const int ew = epi_warps(kp.epi, kp.BN);
-  const KernelFn fn = kp.pair ? select_kernel<true>(kp.epi, ew) : select_kernel<false>(kp.epi, ew);
+  const bool te = tma_epilogue_ok(kp);
+  const int ew = te ? 4 : epi_warps(kp.epi, kp.BN);
+  KernelFn fn;
+  if (te) {
+    fn = kp.pair ? gemm_tc_kernel<OUT_F32, ACT_NONE, true, true, 4, true> : gemm_tc_kernel<OUT_F32, ACT_NONE, true, false, 4, true>;
+    const long long res_rows = kp.epi.res_mod > 0 ? kp.epi.res_mod : kp.M;
+    if (!make_tmap_f32_chunk(&kp.tmR, kp.epi.residual, res_rows, kp.N, kp.epi.ldr)) return cudaErrorInvalidValue;
+    if (!make_tmap_f32_chunk(&kp.tmC, kp.epi.out, kp.M, kp.N, kp.epi.ldc)) return cudaErrorInvalidValue;
+  } else {
+    fn = kp.pair ? select_kernel<true>(kp.epi, ew) : select_kernel<false>(kp.epi, ew);
+  }
   TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
-  const int threads = 64 + 32 * ew;
-  const int staging = ew * 2048;
+  const int threads = 64 + 32 * ew + (te ? 64 : 0);
+  const int staging = te ? kResSlots * kResSlotBytes : ew * 2048;
   const int slots = kp.pair ? max_pairs(reinterpret_cast<const void*>(fn), 200 * 1024, threads) : num_sms();
   if (kp.b_resident && (num_kb * b_bytes > (kp.pair ? kResidentMaxPair : kResidentMax) || kp.num_n_tiles > slots)) kp.b_resident = 0;
   const int res_bytes = kp.b_resident ? num_kb * b_bytes : 0;
@@ -787,8 +928,9 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   if (dbg & 4) cudaMemset(dbg_buf, 0, 16 * sizeof(unsigned long long));
   char tag[128];
   if (prof_enabled()) {
-    std::snprintf(tag, sizeof(tag), "%s M%d N%d K%d BN%d BK%d st%d grid%d %s%s", kp.mode ? "conv" : "lin", kp.M, kp.N,
-                  num_kb * kp.BK, kp.BN, kp.BK, kp.stages, grid, kp.b_resident ? "resident" : "stream", kp.pair ? " pair" : "");
+    std::snprintf(tag, sizeof(tag), "%s M%d N%d K%d BN%d BK%d st%d grid%d %s%s%s", kp.mode ? "conv" : "lin", kp.M, kp.N,
+                  num_kb * kp.BK, kp.BN, kp.BK, kp.stages, grid, kp.b_resident ? "resident" : "stream", kp.pair ? " pair" : "",
+                  te ? " tma-epi" : "");
     prof_record(s, true, 0, 0);
   }
   if (kp.pair) {
