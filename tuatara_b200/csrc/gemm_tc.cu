@@ -180,9 +180,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // TMA loads that run ahead of the MMAs (the register path had one 2 KB segment per warp in flight and the
 // epilogue took 2.6x the mainloop: profiles/r1b_gemm_roles.md), 4 epilogue warps add accumulator + bias to their
 // own rows in place, warp 3 writes the chunk back with a TMA store.  No per-thread global access at all.
-template <int OUT, int ACT, bool RES, bool PAIR, int EW, bool TE = false>
+// TS ("TMA store", bf16 outputs): an epilogue warp writes its 32 rows x 64 B of a segment into a warp-private
+// SWIZZLE_64B smem tile and one lane hands it to a TMA store -- no read-back, no per-thread global stores (the LSU
+// store path cost ~1000 cycles per 128 x 256 tile, profiles/r1b_gemm_roles.md).  Image edges / short last tiles
+// are clipped by the TMA unit.
+template <int OUT, int ACT, bool RES, bool PAIR, int EW, bool TE = false, bool TS = false>
 __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kernel(const __grid_constant__ KParams p) {
   static_assert(!TE || (OUT == OUT_F32 && RES && EW == 4), "TMA epilogue: fp32 out + residual, 4 epilogue warps");
+  static_assert(!TS || (OUT == OUT_BF16 && !RES && !TE), "TMA store epilogue: bf16 outputs");
+  constexpr int kTsBufs = EW == 16 ? 1 : 2;         // 2 KB store tiles per warp (ping-pong with 8 warps)
   constexpr int kThreads = 64 + 32 * EW + (TE ? 64 : 0);
   constexpr int kEpiWarp0 = TE ? 4 : 2;   // first epilogue warp (a multiple of 4 apart from 2: TMEM quadrant = warp & 3)
   constexpr int kEpiWarps = EW;
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
   uint8_t* sBres = smem;                                        // [num_kb][BN rows] when resident
   uint8_t* ring = smem + (resident ? num_kb * b_bytes : 0);
   uint8_t* res_ring = ring + p.stages * stage_bytes;            // TE only
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(res_ring + (TE ? kResSlots * kResSlotBytes : 0));
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(res_ring + (TE ? kResSlots * kResSlotBytes : TS ? EW * kTsBufs * 2048 : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -405,7 +411,10 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
     const int q = warp & 3;                      // TMEM lane quadrant this warp may read
     const int part = (warp - kEpiWarp0) >> 2;    // kParts warps share a quadrant and split the tile's columns
     const int r = q * 32 + lane;                 // tile row == TMEM lane
-    const uint32_t stg = ptx::smem_u32(reinterpret_cast<uint8_t*>(ctl + 1)) + (warp - kEpiWarp0) * 2048;
+    const uint32_t stg = TS ? ptx::smem_u32(res_ring) + (warp - kEpiWarp0) * kTsBufs * 2048
+                            : ptx::smem_u32(reinterpret_cast<uint8_t*>(ctl + 1)) + (warp - kEpiWarp0) * 2048;
+    int ts_buf = 0;
+    (void)ts_buf;
     const uint32_t bias_s = ptx::smem_u32(&ctl->bias[0][0]);
     const uint32_t own_row = stg + lane * 64;
     const int own_sw = (lane >> 1) & 3;          // swizzle of this thread's own row
@@ -425,7 +434,9 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
     const char* const res_base = static_cast<const char*>(p.epi.residual);
     const float* const bias_g = p.epi.bias;
     const int chunks = BN / 16;
-    const int c_begin = (chunks * part + kParts - 1) / kParts, c_end = (chunks * (part + 1) + kParts - 1) / kParts;
+    // TS splits the columns in whole 32-column segments (a TMA store box), the register path in 16-column chunks
+    const int c_begin = TS ? 2 * ((chunks / 2) * part / kParts) : (chunks * part + kParts - 1) / kParts;
+    const int c_end = TS ? 2 * ((chunks / 2) * (part + 1) / kParts) : (chunks * (part + 1) + kParts - 1) / kParts;
     int as = 0;
     uint32_t aphase = 0;
     long long dbg_e_wait = 0, dbg_e_busy = 0, dbg_tiles = 0;
@@ -573,6 +584,19 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
                                                        : make_uint4(0u, 0u, 0u, 0u);
         };
         if constexpr (RES) { if (c_begin < c_end) load_res(c_begin); }
+        // TMA store coordinates of this warp's 32 rows: linear {col, row}; conv {channel, x, y, image}
+        int ts_c1 = 0, ts_c2 = 0, ts_c3 = 0;
+        if constexpr (TS) {
+          if (mode == 1) {
+            const int img = m_tile / per_img, t = m_tile - img * per_img;
+            ts_c1 = (t % tiles_x) * TW;
+            ts_c2 = (t / tiles_x) * TH + q * (32 / TW);
+            ts_c3 = img;
+          } else {
+            ts_c1 = m_tile * kBlockM + q * 32;
+          }
+        }
+        (void)ts_c1; (void)ts_c2; (void)ts_c3;
         { const long long t0 = clock64(); ptx::mbar_wait(&ctl->acc_full[as], aphase); dbg_e_wait += clock64() - t0; }
         const long long dbg_t_busy0 = clock64();
         ptx::tc_fence_after();
@@ -630,14 +654,34 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
                               make_uint4(__float_as_uint(v[4 * k]), __float_as_uint(v[4 * k + 1]),
                                          __float_as_uint(v[4 * k + 2]), __float_as_uint(v[4 * k + 3])));
               } else {
+                if constexpr (TS) {
+                  if (sc == 0) {  // the store issued from this buffer kTsBufs segments ago has finished reading it
+                    if (lane == 0) ptx::bulk_wait_read<kTsBufs - 1>();
+                    __syncwarp();
+                  }
+                }
+                const uint32_t dst_row = TS ? own_row + ts_buf * 2048 : own_row;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                   uint4 o;
                   o.x = pack_bf16(v[8 * k + 0], v[8 * k + 1]); o.y = pack_bf16(v[8 * k + 2], v[8 * k + 3]);
                   o.z = pack_bf16(v[8 * k + 4], v[8 * k + 5]); o.w = pack_bf16(v[8 * k + 6], v[8 * k + 7]);
-                  ptx::sts128(own_row + (((sc * 2 + k) ^ own_sw) << 4), o);
+                  ptx::sts128(dst_row + (((sc * 2 + k) ^ own_sw) << 4), o);
                 }
               }
+            }
+            if constexpr (TS) {
+              ptx::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                if (dbg != 1) {
+                  if (mode == 1) ptx::tma_store_4d_s(&p.tmC, stg + ts_buf * 2048, n0 + c0 * 16, ts_c1, ts_c2, ts_c3);
+                  else ptx::tma_store_2d_s(&p.tmC, stg + ts_buf * 2048, n0 + c0 * 16, ts_c1);
+                }
+                ptx::bulk_commit();
+              }
+              ts_buf ^= kTsBufs - 1;
+              return;
             }
             __syncwarp();
             // coalesced store: 4 lanes x 16 B per row, 8 rows per pass.  (With an odd chunk count the last
@@ -678,6 +722,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
       ++dbg_tiles;
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if constexpr (TS) { if (lane == 0) ptx::bulk_wait<0>(); }
     if ((p.debug & 4) && blockIdx.x == 0 && lane == 0 && (warp == kEpiWarp0 || warp == kEpiWarp0 + 4)) {
       const int o = (warp == kEpiWarp0 + 4) * 3;
       p.dbg_out[5 + o] = dbg_e_wait; p.dbg_out[6 + o] = dbg_e_busy; p.dbg_out[7 + o] = dbg_tiles;
@@ -841,6 +886,18 @@ int epi_warps(const Epilogue& e, int BN) {
 }
 
 template <bool PAIR>
+void (*select_kernel_ts(const Epilogue& e, int ew))(const KParams) {
+  if (ew == 8) {
+    if (e.act == ACT_RELU) return gemm_tc_kernel<OUT_BF16, ACT_RELU, false, PAIR, 8, false, true>;
+    if (e.act == ACT_GELU) return gemm_tc_kernel<OUT_BF16, ACT_GELU, false, PAIR, 8, false, true>;
+    return gemm_tc_kernel<OUT_BF16, ACT_NONE, false, PAIR, 8, false, true>;
+  }
+  if (e.act == ACT_RELU) return gemm_tc_kernel<OUT_BF16, ACT_RELU, false, PAIR, 16, false, true>;
+  if (e.act == ACT_GELU) return gemm_tc_kernel<OUT_BF16, ACT_GELU, false, PAIR, 16, false, true>;
+  return gemm_tc_kernel<OUT_BF16, ACT_NONE, false, PAIR, 16, false, true>;
+}
+
+template <bool PAIR>
 void (*select_kernel(const Epilogue& e, int ew))(const KParams) {
   if (e.out_type == OUT_CLS_TAIL) return gemm_tc_kernel<OUT_CLS_TAIL, ACT_RELU, false, PAIR, 8>;
   if (e.out_type == OUT_F32 && ew == 16)
@@ -893,6 +950,9 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   const int a_bytes = kBlockM * row_bytes, b_bytes = b_rows * row_bytes;
   using KernelFn = void (*)(const KParams);
   const bool te = tma_epilogue_ok(kp);
+  static const int ts_env = env_int("TT_GEMM_TS", 1);
+  const bool ts = !te && ts_env != 0 && kp.epi.out_type == OUT_BF16 && kp.BN % 32 == 0 && kp.epi.ldc % 8 == 0 &&
+                  reinterpret_cast<uintptr_t>(kp.epi.out) % 16 == 0;
   const int ew = te ? 4 : epi_warps(kp.epi, kp.BN);
   KernelFn fn;
   if (te) {
@@ -900,12 +960,27 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
     const long long res_rows = kp.epi.res_mod > 0 ? kp.epi.res_mod : kp.M;
     if (!make_tmap_f32_chunk(&kp.tmR, kp.epi.residual, res_rows, kp.N, kp.epi.ldr)) return cudaErrorInvalidValue;
     if (!make_tmap_f32_chunk(&kp.tmC, kp.epi.out, kp.M, kp.N, kp.epi.ldc)) return cudaErrorInvalidValue;
+  } else if (ts) {
+    fn = kp.pair ? select_kernel_ts<true>(kp.epi, ew) : select_kernel_ts<false>(kp.epi, ew);
+    if (kp.mode == 1) {
+      const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kp.N), static_cast<cuuint64_t>(kp.W), static_cast<cuuint64_t>(kp.H),
+                                  static_cast<cuuint64_t>(kp.M / (kp.H * kp.W))};
+      const cuuint64_t pitch = static_cast<cuuint64_t>(kp.epi.ldc) * 2;
+      const cuuint64_t strides[3] = {pitch, pitch * kp.W, pitch * kp.W * kp.H};
+      const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(kp.TW), static_cast<cuuint32_t>(32 / kp.TW), 1};
+      if (!make_tmap_bf16(&kp.tmC, kp.epi.out, 4, dims, strides, box, 64)) return cudaErrorInvalidValue;
+    } else {
+      const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kp.N), static_cast<cuuint64_t>(kp.M)};
+      const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kp.epi.ldc) * 2};
+      const cuuint32_t box[2] = {32, 32};
+      if (!make_tmap_bf16(&kp.tmC, kp.epi.out, 2, dims, strides, box, 64)) return cudaErrorInvalidValue;
+    }
   } else {
     fn = kp.pair ? select_kernel<true>(kp.epi, ew) : select_kernel<false>(kp.epi, ew);
   }
   TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
   const int threads = 64 + 32 * ew + (te ? 64 : 0);
-  const int staging = te ? kResSlots * kResSlotBytes : ew * 2048;
+  const int staging = te ? kResSlots * kResSlotBytes : ts ? ew * (ew == 16 ? 1 : 2) * 2048 : ew * 2048;
   const int slots = kp.pair ? max_pairs(reinterpret_cast<const void*>(fn), 200 * 1024, threads) : num_sms();
   if (kp.b_resident && (num_kb * b_bytes > (kp.pair ? kResidentMaxPair : kResidentMax) || kp.num_n_tiles > slots)) kp.b_resident = 0;
   const int res_bytes = kp.b_resident ? num_kb * b_bytes : 0;
@@ -930,7 +1005,7 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   if (prof_enabled()) {
     std::snprintf(tag, sizeof(tag), "%s M%d N%d K%d BN%d BK%d st%d grid%d %s%s%s", kp.mode ? "conv" : "lin", kp.M, kp.N,
                   num_kb * kp.BK, kp.BN, kp.BK, kp.stages, grid, kp.b_resident ? "resident" : "stream", kp.pair ? " pair" : "",
-                  te ? " tma-epi" : "");
+                  te ? " tma-epi" : ts ? " tma-store" : "");
     prof_record(s, true, 0, 0);
   }
   if (kp.pair) {
