@@ -166,3 +166,14 @@ def test_linear_residual_in_place(native_lib, M, K, N):
                                    x.data_ptr(), 1, N, 0, 0, None), "tt_linear_dev")
     torch.cuda.synchronize()
     _check(x.cpu(), ref, K, f"in-place residual linear M{M} K{K} N{N}")
+
+
+@pytest.mark.parametrize("B,H,W,C0,Cout", [
+    (1, 32, 48, 64, 64), (2, 40, 24, 64, 32), (1, 64, 64, 128, 128), (3, 17, 9, 128, 64), (1, 128, 136, 64, 64),
+    (1, 16, 8, 64, 16), (2, 50, 70, 128, 64), (8, 64, 64, 64, 128),
+])
+def test_conv_halo(native_lib, B, H, W, C0, Cout):
+    """3x3 convs with resident weights run in halo mode: one staged (16+2) x 16-pixel tile per 64 channels feeds all
+    nine taps (the tap's A operand is that tile read at a pixel offset); borders, odd sizes, 1 and 2 channel blocks."""
+    out, ref = _conv(native_lib, B, H, W, C0, 0, Cout, 9, 1)
+    _check(out.reshape(-1, Cout), ref.reshape(-1, Cout), 9 * C0, f"halo conv {B}x{H}x{W} C{C0}->{Cout}")

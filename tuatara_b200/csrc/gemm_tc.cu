@@ -46,6 +46,9 @@ constexpr int kResidentMaxPair = 100 * 1024;  // PAIR: half of a 256 x 384 slice
 constexpr int kStagingBytes = kMaxEpiWarps * 2048;  // epilogue transpose tiles, 2 KB per warp (upper bound, used for planning)
 // TMA epilogue (fp32 residual GEMMs): ring of [128 rows x 32 fp32] SWIZZLE_128B chunks that the residual is loaded
 // into, updated in place by the epilogue warps and stored from
+constexpr int kHaloPitch = 16;                               // pixels per staged halo row (tile width 8 + 2, padded: SBO = 2048)
+constexpr int kHaloRows = 18;                                // tile height 16 + 2
+constexpr int kHaloBytes = kHaloRows * kHaloPitch * 128;     // one 64-channel block: 36 KB
 constexpr int kResSlots = 4;
 constexpr int kResSlotBytes = 128 * 128;
 
@@ -61,6 +64,8 @@ struct KParams {
   int num_m_tiles, num_n_tiles;  // num_m_tiles counts scheduling units: 128-row tiles, or 256-row pairs in PAIR mode
   int m_tiles_total;             // 128-row tiles that exist (PAIR: the last pair may have only one)
   int pair;
+  int halo;        // conv, 3x3 dil 1, Cin 64/128, weights resident: one (TH+2) x 16-pixel halo tile per 64-channel block
+                   // feeds all 9 taps (A operand = the staged tile read at a pixel offset); 0 = one TMA box per tap
   int stages;
   int b_resident;  // 1: the CTA's [BN x K] weight slice is loaded once and stays in smem; only A streams
   int debug;       // TT_GEMM_DEBUG (development only): 1 = skip epilogue stores, 2 = skip TMEM loads + math + stores
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
   const int kb_per_tap = p.kb_src[0] + p.kb_src[1];
   const int num_kb = p.taps * kb_per_tap;
   const bool resident = p.b_resident != 0;
-  const int stage_bytes = resident ? a_bytes : a_bytes + b_bytes;
+  const int stage_bytes = p.halo ? kHaloBytes : resident ? a_bytes : a_bytes + b_bytes;
   uint8_t* sBres = smem;                                        // [num_kb][BN rows] when resident
   uint8_t* ring = smem + (resident ? num_kb * b_bytes : 0);
   uint8_t* res_ring = ring + p.stages * stage_bytes;            // TE only
@@ -282,6 +287,18 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
           y0 = (t / p.tiles_x) * p.TH;
           x0 = (t % p.tiles_x) * p.TW;
         }
+        if (p.halo) {
+          // one halo block per 64 input channels: pixels (x0-1 .. x0+14, y0-1 .. y0+16), out-of-image = zero padding
+          for (int cb = 0; cb < p.kb_src[0]; ++cb) {
+            ptx::mbar_wait(&ctl->empty[stage], phase ^ 1);
+            uint8_t* sA = ring + stage * stage_bytes;
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&ctl->full[stage], tx_mult * static_cast<uint32_t>(kHaloBytes));
+            if constexpr (PAIR) ptx::tma_load_4d_pair(sA, &p.tmA[0], full0_c + stage * 8, cb * p.BK, x0 - 1, y0 - 1, img);
+            else ptx::tma_load_4d(sA, &p.tmA[0], &ctl->full[stage], cb * p.BK, x0 - 1, y0 - 1, img);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         int kb = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = (p.taps == 9) ? (tap / 3 - 1) * p.dil : 0;
@@ -337,6 +354,31 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
         { const long long t0 = clock64(); ptx::mbar_wait(&ctl->acc_empty[as], aphase ^ 1); dbg_w_acc += clock64() - t0; }
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * kAccStride;
+        if (p.halo) {
+          for (int cb = 0; cb < p.kb_src[0]; ++cb) {
+            { const long long t0 = clock64(); ptx::mbar_wait(&ctl->full[stage], phase); dbg_w_full += clock64() - t0; }
+            ptx::tc_fence_after();
+            const uint32_t h_addr = ptx::smem_u32(ring + stage * stage_bytes);
+            for (int tap = 0; tap < 9; ++tap) {
+              const int ty = tap / 3, tx = tap - 3 * ty;
+              const uint32_t a_addr = h_addr + (ty * kHaloPitch + tx) * 128;   // output pixel (y, x) reads halo pixel (y + ty, x + tx)
+              const uint32_t b_addr = ptx::smem_u32(sBres + (tap * p.kb_src[0] + cb) * b_bytes);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * 32, kHaloPitch * 128, 0);
+                const uint64_t db = ptx::make_smem_desc(b_addr + k * 32, row_bytes);
+                if constexpr (PAIR) ptx::mma_bf16_pair(d_tmem, da, db, idesc, (cb | tap | k) != 0);
+                else ptx::mma_bf16(d_tmem, da, db, idesc, (cb | tap | k) != 0);
+              }
+            }
+            if constexpr (PAIR) ptx::mma_commit_pair(&ctl->empty[stage], 3);
+            else ptx::mma_commit(&ctl->empty[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+          if constexpr (PAIR) ptx::mma_commit_pair(&ctl->acc_full[as], 3);
+          else ptx::mma_commit(&ctl->acc_full[as]);
+          if (++as == 2) { as = 0; aphase ^= 1; }
+          continue;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           { const long long t0 = clock64(); ptx::mbar_wait(&ctl->full[stage], phase); dbg_w_full += clock64() - t0; }
           ptx::tc_fence_after();
@@ -984,7 +1026,8 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   const int slots = kp.pair ? max_pairs(reinterpret_cast<const void*>(fn), 200 * 1024, threads) : num_sms();
   if (kp.b_resident && (num_kb * b_bytes > (kp.pair ? kResidentMaxPair : kResidentMax) || kp.num_n_tiles > slots)) kp.b_resident = 0;
   const int res_bytes = kp.b_resident ? num_kb * b_bytes : 0;
-  const int stage_bytes = kp.b_resident ? a_bytes : a_bytes + b_bytes;
+  if (kp.halo && !kp.b_resident) { set_error("conv: halo mode needs resident weights"); return cudaErrorInvalidValue; }
+  const int stage_bytes = kp.halo ? kHaloBytes : kp.b_resident ? a_bytes : a_bytes + b_bytes;
   kp.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - staging - 1024 - res_bytes) / stage_bytes));
   const size_t smem = static_cast<size_t>(res_bytes) + static_cast<size_t>(kp.stages) * stage_bytes + sizeof(SmemCtl) + staging + 1024;
   int grid;  // in scheduling slots: CTAs, or CTA pairs
@@ -1005,7 +1048,7 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   if (prof_enabled()) {
     std::snprintf(tag, sizeof(tag), "%s M%d N%d K%d BN%d BK%d st%d grid%d %s%s%s", kp.mode ? "conv" : "lin", kp.M, kp.N,
                   num_kb * kp.BK, kp.BN, kp.BK, kp.stages, grid, kp.b_resident ? "resident" : "stream", kp.pair ? " pair" : "",
-                  te ? " tma-epi" : ts ? " tma-store" : "");
+                  kp.halo ? " halo" : te ? " tma-epi" : ts ? " tma-store" : "");
     prof_record(s, true, 0, 0);
   }
   if (kp.pair) {
@@ -1076,8 +1119,21 @@ cudaError_t conv_forward(const ConvProblem& c, const Epilogue& e, cudaStream_t s
   if (c.taps != 1 && c.taps != 9) { set_error("conv: taps must be 1 or 9"); return cudaErrorInvalidValue; }
   kp.mode = 1;
   kp.H = c.H; kp.W = c.W;
+  // Halo mode (3x3, dilation 1, one source of 64 or 128 channels, weights small enough to stay resident): the
+  // per-tap boxes re-read every input pixel 9 times from L2 and these narrow layers were bound by exactly that
+  // traffic (c1_2: 361 TF).  The tile becomes 16 x 8 pixels so that every 8-row MMA group is one image row.
+  static const int halo_env = env_int("TT_CONV_HALO", 1);
+  {
+    const int cout_pad = ((c.Cout + 15) / 16) * 16;
+    const long long w_bytes = static_cast<long long>(cout_pad) * c.taps * ctot * 2;
+    const bool pair_ok = c.pair != 0 && (cout_pad / 2) % 8 == 0 && e.out_type != OUT_CLS_TAIL;
+    const bool fits = w_bytes <= kResidentMax || (pair_ok && w_bytes / 2 <= kResidentMaxPair);
+    kp.halo = (halo_env != 0 && c.taps == 9 && c.dil == 1 && c.nsrc == 1 && kp.BK == 64 && ctot <= 128 && cout_pad <= 256 &&
+               c.Cout % 16 == 0 && c.BN == 0 && c.resident != 0 && fits && c.W >= 8 && c.H >= 16)
+                  ? 1 : 0;
+  }
   // 128 output pixels per tile as a TH x TW rectangle; wider-than-tall keeps TMA rows long
-  kp.TW = c.W >= 16 ? 16 : 8;
+  kp.TW = (c.W >= 16 && !kp.halo) ? 16 : 8;
   kp.TH = kBlockM / kp.TW;
   kp.tiles_x = (c.W + kp.TW - 1) / kp.TW;
   kp.tiles_y = (c.H + kp.TH - 1) / kp.TH;
@@ -1090,6 +1146,13 @@ cudaError_t conv_forward(const ConvProblem& c, const Epilogue& e, cudaStream_t s
     kp.b_resident = c.BN ? (c.resident == 1) : pl.resident;
     kp.pair = c.BN ? (c.pair == 1) : pl.pair;
     if (kp.pair && ((kp.BN / 2) % 8 != 0 || e.out_type == OUT_CLS_TAIL)) kp.pair = 0;
+    if (kp.halo) {  // the whole Cout in one resident tile; a CTA pair when the slice only fits halved
+      kp.BN = c.Cout;
+      kp.b_resident = 1;
+      const long long w_bytes = static_cast<long long>(c.Cout) * c.taps * ctot * 2;
+      const bool pair_ok = c.pair != 0 && (c.Cout / 2) % 8 == 0 && e.out_type != OUT_CLS_TAIL;
+      kp.pair = (w_bytes > kResidentMax || (pair_ok && pl.pair)) && pair_ok ? 1 : 0;
+    }
   }
   kp.num_n_tiles = (c.Cout + kp.BN - 1) / kp.BN;
   kp.taps = c.taps; kp.dil = c.dil;
@@ -1103,8 +1166,8 @@ cudaError_t conv_forward(const ConvProblem& c, const Epilogue& e, cudaStream_t s
                                 static_cast<cuuint64_t>(c.H), static_cast<cuuint64_t>(c.batch)};
     const cuuint64_t pitch = static_cast<cuuint64_t>(c.src[i].pitch) * 2;
     const cuuint64_t strides[3] = {pitch, pitch * c.W, pitch * c.W * c.H};
-    const cuuint32_t box[4] = {static_cast<cuuint32_t>(kp.BK), static_cast<cuuint32_t>(kp.TW),
-                               static_cast<cuuint32_t>(kp.TH), 1};
+    const cuuint32_t box[4] = {static_cast<cuuint32_t>(kp.BK), static_cast<cuuint32_t>(kp.halo ? kHaloPitch : kp.TW),
+                               static_cast<cuuint32_t>(kp.halo ? kHaloRows : kp.TH), 1};
     if (!make_map(&kp.tmA[i], c.src[i].ptr, 4, dims, strides, box, row_bytes)) return cudaErrorInvalidValue;
   }
   {

@@ -275,6 +275,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_
   d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : 4) << 61; // swizzle mode
   return d;
 }
+// Same for a SWIZZLE_128B K-major tile whose 8-row groups are `sbo_bytes` apart.  Used by the halo convolution:
+// a tap's A operand is the staged (TH+2) x 16-pixel tile read at a pixel offset, so the start address is NOT
+// 1024-byte aligned.  Measured on B200 (tests/test_gemm_gpu.py::test_conv_halo): the tensor core applies the
+// 128B-swizzle XOR to the absolute smem address bits, exactly as TMA wrote the tile, and the descriptor's
+// matrix-base-offset field (bits [49,52)) must stay 0 -- setting it to the row offset gives wrong products.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_off & 7) << 49;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accum, bf16 A/B, both K-major.
 __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
