@@ -407,6 +407,7 @@ def run_native(args, rank, local_rank, world):
                                "(canvas 1024), CRAFT output overridden by the page's synthetic score map after CRAFT ran",
                    "pages_per_gpu_per_step": n, "craft_batch_pages": args.batch_pages, "crops_per_page": WORDS,
                    "weights": "seeded random init (CRAFT VGG16-BN, PARSeq-base)", "parallelism": f"dp{world} (pages)",
+                   "kernel_paths": "conservative (retry after a failed first attempt)" if os.environ.get("TT_BENCH_RETRY") else "default",
                    "l2": f"inputs larger than L2: {n * PAGE * PAGE * 3 / 2**20:.0f} MiB of distinct pages per step"},
         "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": r_host["h2d"], "d2h_bytes_per_step": r_host["d2h"],
                 "ms_per_step": r_host["ms"] / args.steps},
@@ -437,6 +438,40 @@ def run_native(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def supervise(args) -> bool:
+    """Runs the native arm in a child process with a time budget.  A kernel-side protocol bug would otherwise hang
+    the whole benchmark (device waits are bounded and trap after 4 s, which poisons the CUDA context): the parent
+    kills the exact process group it started and retries once with the conservative kernel paths (per-tap conv
+    boxes, register epilogues).  Under torchrun every rank supervises its own child."""
+    if os.environ.get("TT_BENCH_CHILD") == "1":
+        return False
+    import signal
+
+    budget = 240 + 20 * (args.steps + args.warmup)
+    attempts = [{}, {"TT_CONV_HALO": "0", "TT_GEMM_TS": "0", "TT_GEMM_TE": "0", "TT_BENCH_RETRY": "1"}]
+    for extra in attempts:
+        env = dict(os.environ, TT_BENCH_CHILD="1", **extra)
+        p = subprocess.Popen([sys.executable, str(Path(__file__).resolve()), *sys.argv[1:]], env=env, stdout=subprocess.PIPE,
+                             start_new_session=True)
+        try:
+            out, _ = p.communicate(timeout=budget)
+        except subprocess.TimeoutExpired:
+            try:
+                os.killpg(p.pid, signal.SIGKILL)  # the session this call created, nothing else
+            except ProcessLookupError:
+                pass
+            p.wait()
+            print(f"bench.py: child exceeded {budget} s, retrying", file=sys.stderr, flush=True)
+            continue
+        text = out.decode(errors="replace")
+        if p.returncode == 0 and (env_int("RANK", 0) != 0 or '"metric"' in text):
+            sys.stdout.write(text)
+            sys.stdout.flush()
+            return True
+        print(f"bench.py: child failed (rc {p.returncode}), retrying", file=sys.stderr, flush=True)
+    raise SystemExit("bench.py: native arm failed twice")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -450,7 +485,7 @@ def main():
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
-    else:
+    elif not supervise(args):
         run_native(args, rank, local_rank, world)
 
 

@@ -170,7 +170,7 @@ def test_linear_residual_in_place(native_lib, M, K, N):
 
 @pytest.mark.parametrize("B,H,W,C0,Cout", [
     (1, 32, 48, 64, 64), (2, 40, 24, 64, 32), (1, 64, 64, 128, 128), (3, 17, 9, 128, 64), (1, 128, 136, 64, 64),
-    (1, 16, 8, 64, 16), (2, 50, 70, 128, 64), (8, 64, 64, 64, 128),
+    (1, 16, 8, 64, 16), (2, 50, 70, 128, 64), (8, 64, 64, 64, 128), (1, 64, 64, 32, 32), (2, 33, 41, 32, 16), (1, 96, 128, 32, 64),
 ])
 def test_conv_halo(native_lib, B, H, W, C0, Cout):
     """3x3 convs with resident weights run in halo mode: one staged (16+2) x 16-pixel tile per 64 channels feeds all

@@ -1,2 +1,7 @@
 #!/bin/bash
-for v in 1 2; do echo "== TT_CONV_HALO=$v"; TT_CONV_HALO=$v timeout 300 python -m pytest tests/test_gemm_gpu.py -x -q -k "halo" 2>&1 | grep -E "Error|passed|failed" | cut -c1-500; done
+for shape in "8 1024 1024 64 64" "8 512 512 64 128" "8 512 512 64 32" "8 512 512 32 32"; do
+  for halo in 1 0; do
+    TT_CONV_HALO=$halo python tools/conv_probe.py $shape 5 2>&1 | grep -v Warn | sed "s/^/halo=$halo /"
+    for dbg in 4 6; do TT_CONV_HALO=$halo TT_GEMM_DEBUG=$dbg python tools/conv_probe.py $shape 1 2>&1 | grep "gemm dbg" | tail -1 | sed "s/^/halo=$halo dbg=$dbg /"; done
+  done
+done

@@ -48,7 +48,8 @@ constexpr int kStagingBytes = kMaxEpiWarps * 2048;  // epilogue transpose tiles,
 // into, updated in place by the epilogue warps and stored from
 constexpr int kHaloPitch = 16;                               // pixels per staged halo row (tile width 8 + 2, padded: SBO = 2048)
 constexpr int kHaloRows = 18;                                // tile height 16 + 2
-constexpr int kHaloBytes = kHaloRows * kHaloPitch * 128;     // one 64-channel block: 36 KB
+constexpr int kHaloPixels = kHaloRows * kHaloPitch;           // x 128 B (64 channels) = 36 KB, x 64 B (32 channels) = 18 KB
+constexpr int kHaloResidentMax = 82 * 1024;                  // weights that leave room for 3 halo stages in one CTA
 constexpr int kResSlots = 4;
 constexpr int kResSlotBytes = 128 * 128;
 
@@ -204,17 +205,18 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
   const int row_bytes = p.BK * 2;
   const int a_bytes = kBlockM * row_bytes;
   const int b_bytes = (PAIR ? p.BN / 2 : p.BN) * row_bytes;   // this CTA's share of the weight tile
-  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0;    // 0 = leader (issues the MMAs)
+  // warp-uniform by construction (shfl from lane 0): the producer / MMA warps must stay in the uniform datapath
+  const uint32_t rank = PAIR ? __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0) : 0;    // 0 = leader (issues the MMAs)
   const int kb_per_tap = p.kb_src[0] + p.kb_src[1];
   const int num_kb = p.taps * kb_per_tap;
   const bool resident = p.b_resident != 0;
-  const int stage_bytes = p.halo ? kHaloBytes : resident ? a_bytes : a_bytes + b_bytes;
+  const int stage_bytes = p.halo ? kHaloPixels * row_bytes : resident ? a_bytes : a_bytes + b_bytes;
   uint8_t* sBres = smem;                                        // [num_kb][BN rows] when resident
   uint8_t* ring = smem + (resident ? num_kb * b_bytes : 0);
   uint8_t* res_ring = ring + p.stages * stage_bytes;            // TE only
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(res_ring + (TE ? kResSlots * kResSlotBytes : TS ? EW * kTsBufs * 2048 : 0));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -252,25 +254,25 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
   __syncthreads();
   if constexpr (PAIR) ptx::cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   ptx::tc_fence_after();
-  const uint32_t tmem_base = ctl->tmem_base;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    {  // all 32 lanes run the loops converged; one elected lane issues (see ptx.cuh "_e")
       TileIter it(p);
       const int b_rows = PAIR ? p.BN / 2 : p.BN;
       const int b_row0 = static_cast<int>(rank) * b_rows;           // this CTA's rows inside the BN-row weight tile
       const uint32_t tx_mult = PAIR ? 2u : 1u;                      // the leader's barrier counts both CTAs' bytes
       uint32_t bfull_c = 0, full0_c = 0;                            // PAIR: the leader's barriers as shared::cluster addresses
       if constexpr (PAIR) {
-        bfull_c = ptx::mapa(ptx::smem_u32(&ctl->b_full), 0);
-        full0_c = ptx::mapa(ptx::smem_u32(&ctl->full[0]), 0);
+        bfull_c = __shfl_sync(0xffffffffu, ptx::mapa(ptx::smem_u32(&ctl->b_full), 0), 0);
+        full0_c = __shfl_sync(0xffffffffu, ptx::mapa(ptx::smem_u32(&ctl->full[0]), 0), 0);
       }
       if (resident && it.valid()) {
-        if (rank == 0) ptx::mbar_arrive_expect_tx(&ctl->b_full, tx_mult * static_cast<uint32_t>(num_kb * b_bytes));
+        if (rank == 0) ptx::mbar_arrive_expect_tx_e(&ctl->b_full, tx_mult * static_cast<uint32_t>(num_kb * b_bytes));
         for (int kb = 0; kb < num_kb; ++kb) {
-          if constexpr (PAIR) ptx::tma_load_2d_pair(sBres + kb * b_bytes, &p.tmB, bfull_c, kb * p.BK, it.n_tile(p) * p.BN + b_row0);
-          else ptx::tma_load_2d(sBres + kb * b_bytes, &p.tmB, &ctl->b_full, kb * p.BK, it.n_tile(p) * p.BN);
+          if constexpr (PAIR) ptx::tma_load_2d_pair_e(sBres + kb * b_bytes, &p.tmB, bfull_c, kb * p.BK, it.n_tile(p) * p.BN + b_row0);
+          else ptx::tma_load_2d_e(sBres + kb * b_bytes, &p.tmB, &ctl->b_full, kb * p.BK, it.n_tile(p) * p.BN);
         }
       }
       int stage = 0;
@@ -290,11 +292,11 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
         if (p.halo) {
           // one halo block per 64 input channels: pixels (x0-1 .. x0+14, y0-1 .. y0+16), out-of-image = zero padding
           for (int cb = 0; cb < p.kb_src[0]; ++cb) {
-            ptx::mbar_wait(&ctl->empty[stage], phase ^ 1);
+            ptx::mbar_wait(&ctl->empty[stage], phase ^ 1); __syncwarp();
             uint8_t* sA = ring + stage * stage_bytes;
-            if (rank == 0) ptx::mbar_arrive_expect_tx(&ctl->full[stage], tx_mult * static_cast<uint32_t>(kHaloBytes));
-            if constexpr (PAIR) ptx::tma_load_4d_pair(sA, &p.tmA[0], full0_c + stage * 8, cb * p.BK, x0 - 1, y0 - 1, img);
-            else ptx::tma_load_4d(sA, &p.tmA[0], &ctl->full[stage], cb * p.BK, x0 - 1, y0 - 1, img);
+            if (rank == 0) ptx::mbar_arrive_expect_tx_e(&ctl->full[stage], tx_mult * static_cast<uint32_t>(stage_bytes));
+            if constexpr (PAIR) ptx::tma_load_4d_pair_e(sA, &p.tmA[0], full0_c + stage * 8, cb * p.BK, x0 - 1, y0 - 1, img);
+            else ptx::tma_load_4d_e(sA, &p.tmA[0], &ctl->full[stage], cb * p.BK, x0 - 1, y0 - 1, img);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
           continue;
@@ -305,23 +307,23 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
           const int dx = (p.taps == 9) ? (tap % 3 - 1) * p.dil : 0;
           for (int src = 0; src < 2; ++src) {
             for (int cb = 0; cb < p.kb_src[src]; ++cb, ++kb) {
-              { const long long t0 = clock64(); ptx::mbar_wait(&ctl->empty[stage], phase ^ 1); dbg_prod_wait += clock64() - t0; }
+              { const long long t0 = clock64(); ptx::mbar_wait(&ctl->empty[stage], phase ^ 1); __syncwarp(); dbg_prod_wait += clock64() - t0; }
               uint8_t* sA = ring + stage * stage_bytes;
-              if (rank == 0) ptx::mbar_arrive_expect_tx(&ctl->full[stage], tx_mult * static_cast<uint32_t>(stage_bytes));
+              if (rank == 0) ptx::mbar_arrive_expect_tx_e(&ctl->full[stage], tx_mult * static_cast<uint32_t>(stage_bytes));
               if constexpr (PAIR) {
                 const uint32_t full_bar = full0_c + stage * 8;
                 // a pair's second tile may not exist (odd tile count): its box is out of bounds and arrives as zeros
                 if (p.mode == 1)
-                  ptx::tma_load_4d_pair(sA, &p.tmA[src], full_bar, cb * p.BK, x0 + dx, y0 + dy, img);
+                  ptx::tma_load_4d_pair_e(sA, &p.tmA[src], full_bar, cb * p.BK, x0 + dx, y0 + dy, img);
                 else
-                  ptx::tma_load_2d_pair(sA, &p.tmA[src], full_bar, cb * p.BK, m_tile * kBlockM);
-                if (!resident) ptx::tma_load_2d_pair(sA + a_bytes, &p.tmB, full_bar, kb * p.BK, n_tile * p.BN + b_row0);
+                  ptx::tma_load_2d_pair_e(sA, &p.tmA[src], full_bar, cb * p.BK, m_tile * kBlockM);
+                if (!resident) ptx::tma_load_2d_pair_e(sA + a_bytes, &p.tmB, full_bar, kb * p.BK, n_tile * p.BN + b_row0);
               } else {
                 if (p.mode == 1)
-                  ptx::tma_load_4d(sA, &p.tmA[src], &ctl->full[stage], cb * p.BK, x0 + dx, y0 + dy, img);
+                  ptx::tma_load_4d_e(sA, &p.tmA[src], &ctl->full[stage], cb * p.BK, x0 + dx, y0 + dy, img);
                 else
-                  ptx::tma_load_2d(sA, &p.tmA[src], &ctl->full[stage], cb * p.BK, m_tile * kBlockM);
-                if (!resident) ptx::tma_load_2d(sA + a_bytes, &p.tmB, &ctl->full[stage], kb * p.BK, n_tile * p.BN);
+                  ptx::tma_load_2d_e(sA, &p.tmA[src], &ctl->full[stage], cb * p.BK, m_tile * kBlockM);
+                if (!resident) ptx::tma_load_2d_e(sA + a_bytes, &p.tmB, &ctl->full[stage], kb * p.BK, n_tile * p.BN);
               }
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
@@ -331,15 +333,15 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
       if constexpr (PAIR) {
         // drain: the leader's last commits still arrive on this CTA's empty barriers; do not exit before they landed
         for (int i = 0; i < p.stages; ++i) {
-          ptx::mbar_wait(&ctl->empty[stage], phase ^ 1);
+          ptx::mbar_wait(&ctl->empty[stage], phase ^ 1); __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if ((p.debug & 4) && blockIdx.x == 0) { p.dbg_out[0] = dbg_prod_wait; p.dbg_out[1] = clock64() - dbg_t_start; }
+      if ((p.debug & 4) && blockIdx.x == 0 && lane == 0) { p.dbg_out[0] = dbg_prod_wait; p.dbg_out[1] = clock64() - dbg_t_start; }
     }
   } else if (warp == 1) {
     // --------------------------------------------------------------- MMA issuer
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {  // all 32 lanes converged, one elected lane issues
       const uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, p.BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -352,57 +354,57 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
       const long long dbg_t_start = clock64();
       for (; it.valid(); it.next()) {
         { const long long t0 = clock64(); ptx::mbar_wait(&ctl->acc_empty[as], aphase ^ 1); dbg_w_acc += clock64() - t0; }
-        ptx::tc_fence_after();
+        __syncwarp(); ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * kAccStride;
         if (p.halo) {
           for (int cb = 0; cb < p.kb_src[0]; ++cb) {
             { const long long t0 = clock64(); ptx::mbar_wait(&ctl->full[stage], phase); dbg_w_full += clock64() - t0; }
-            ptx::tc_fence_after();
+            __syncwarp(); ptx::tc_fence_after();
             const uint32_t h_addr = ptx::smem_u32(ring + stage * stage_bytes);
             for (int tap = 0; tap < 9; ++tap) {
               const int ty = tap / 3, tx = tap - 3 * ty;
-              const uint32_t a_addr = h_addr + (ty * kHaloPitch + tx) * 128;   // output pixel (y, x) reads halo pixel (y + ty, x + tx)
+              const uint32_t a_addr = h_addr + (ty * kHaloPitch + tx) * row_bytes;   // output pixel (y, x) reads halo pixel (y + ty, x + tx)
               const uint32_t b_addr = ptx::smem_u32(sBres + (tap * p.kb_src[0] + cb) * b_bytes);
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t da = ptx::make_smem_desc_sw128(a_addr + k * 32, kHaloPitch * 128, 0);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t da = ptx::make_smem_desc_sbo(a_addr + k * 32, row_bytes, kHaloPitch * row_bytes);
                 const uint64_t db = ptx::make_smem_desc(b_addr + k * 32, row_bytes);
-                if constexpr (PAIR) ptx::mma_bf16_pair(d_tmem, da, db, idesc, (cb | tap | k) != 0);
-                else ptx::mma_bf16(d_tmem, da, db, idesc, (cb | tap | k) != 0);
+                if constexpr (PAIR) ptx::mma_bf16_pair_e(d_tmem, da, db, idesc, (cb | tap | k) != 0);
+                else ptx::mma_bf16_e(d_tmem, da, db, idesc, (cb | tap | k) != 0);
               }
             }
-            if constexpr (PAIR) ptx::mma_commit_pair(&ctl->empty[stage], 3);
-            else ptx::mma_commit(&ctl->empty[stage]);
+            if constexpr (PAIR) ptx::mma_commit_pair_e(&ctl->empty[stage], 3);
+            else ptx::mma_commit_e(&ctl->empty[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          if constexpr (PAIR) ptx::mma_commit_pair(&ctl->acc_full[as], 3);
-          else ptx::mma_commit(&ctl->acc_full[as]);
+          if constexpr (PAIR) ptx::mma_commit_pair_e(&ctl->acc_full[as], 3);
+          else ptx::mma_commit_e(&ctl->acc_full[as]);
           if (++as == 2) { as = 0; aphase ^= 1; }
           continue;
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           { const long long t0 = clock64(); ptx::mbar_wait(&ctl->full[stage], phase); dbg_w_full += clock64() - t0; }
-          ptx::tc_fence_after();
+          __syncwarp(); ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(ring + stage * stage_bytes);
           const uint32_t b_addr = resident ? ptx::smem_u32(sBres + kb * b_bytes) : a_addr + a_bytes;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t da = ptx::make_smem_desc(a_addr + k * 32, row_bytes);
             const uint64_t db = ptx::make_smem_desc(b_addr + k * 32, row_bytes);
-            if constexpr (PAIR) ptx::mma_bf16_pair(d_tmem, da, db, idesc, (kb | k) != 0);
-            else ptx::mma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+            if constexpr (PAIR) ptx::mma_bf16_pair_e(d_tmem, da, db, idesc, (kb | k) != 0);
+            else ptx::mma_bf16_e(d_tmem, da, db, idesc, (kb | k) != 0);
           }
-          if constexpr (PAIR) ptx::mma_commit_pair(&ctl->empty[stage], 3);   // frees the stage in both CTAs
-          else ptx::mma_commit(&ctl->empty[stage]);
+          if constexpr (PAIR) ptx::mma_commit_pair_e(&ctl->empty[stage], 3);   // frees the stage in both CTAs
+          else ptx::mma_commit_e(&ctl->empty[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        if constexpr (PAIR) ptx::mma_commit_pair(&ctl->acc_full[as], 3);      // both CTAs' epilogues may drain
-        else ptx::mma_commit(&ctl->acc_full[as]);
+        if constexpr (PAIR) ptx::mma_commit_pair_e(&ctl->acc_full[as], 3);      // both CTAs' epilogues may drain
+        else ptx::mma_commit_e(&ctl->acc_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
-      if ((p.debug & 4) && blockIdx.x == 0) { p.dbg_out[2] = dbg_w_acc; p.dbg_out[3] = dbg_w_full; p.dbg_out[4] = clock64() - dbg_t_start; }
+      if ((p.debug & 4) && blockIdx.x == 0 && lane == 0) { p.dbg_out[2] = dbg_w_acc; p.dbg_out[3] = dbg_w_full; p.dbg_out[4] = clock64() - dbg_t_start; }
     }
   } else if (TE && warp == 2) {
     // ------------------------------------------------- residual loader (TMA epilogue)
-    if (lane == 0) {
+    {
       int slot = 0;
       uint32_t ph = 0;
       for (TileIter it(p); it.valid(); it.next()) {
@@ -410,35 +412,37 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
         const int n0 = it.n_tile(p) * p.BN, m0 = m_tile * kBlockM;
         const int rrow = p.epi.res_mod > 0 ? m0 % p.epi.res_mod : m0;
         for (int c = 0; c < p.BN / 32; ++c) {
-          ptx::mbar_wait(&ctl->res_empty[slot], ph ^ 1);
-          ptx::mbar_arrive_expect_tx(&ctl->res_full[slot], kResSlotBytes);
+          ptx::mbar_wait(&ctl->res_empty[slot], ph ^ 1); __syncwarp();
+          ptx::mbar_arrive_expect_tx_e(&ctl->res_full[slot], kResSlotBytes);
           // a pair's second tile may not exist, columns may end before the tile does: out-of-bounds parts arrive as zeros
-          ptx::tma_load_2d(res_ring + slot * kResSlotBytes, &p.tmR, &ctl->res_full[slot], n0 + c * 32, rrow);
+          ptx::tma_load_2d_e(res_ring + slot * kResSlotBytes, &p.tmR, &ctl->res_full[slot], n0 + c * 32, rrow);
           if (++slot == kResSlots) { slot = 0; ph ^= 1; }
         }
       }
     }
   } else if (TE && warp == 3) {
     // --------------------------------------------------- output storer (TMA epilogue)
-    if (lane == 0) {
+    {
       int slot = 0, prev = -1;
       uint32_t ph = 0;
       for (TileIter it(p); it.valid(); it.next()) {
         const int m_tile = PAIR ? it.m_tile(p) * 2 + static_cast<int>(rank) : it.m_tile(p);
         const int n0 = it.n_tile(p) * p.BN, m0 = m_tile * kBlockM;
         for (int c = 0; c < p.BN / 32; ++c) {
-          ptx::mbar_wait(&ctl->chunk_done[slot], ph);
-          if ((p.debug & 3) == 0) ptx::tma_store_2d(&p.tmC, res_ring + slot * kResSlotBytes, n0 + c * 32, m0);  // rows/cols past the tensor are clipped
-          ptx::bulk_commit();
+          ptx::mbar_wait(&ctl->chunk_done[slot], ph); __syncwarp();
+          if ((p.debug & 3) == 0) ptx::tma_store_2d_e(&p.tmC, res_ring + slot * kResSlotBytes, n0 + c * 32, m0);  // rows/cols past the tensor are clipped
+          ptx::bulk_commit_e();
           if (prev >= 0) {
-            ptx::bulk_wait_read<1>();             // the previous chunk's store has finished reading its slot
-            ptx::mbar_arrive(&ctl->res_empty[prev]);
+            if (ptx::elect_one()) ptx::bulk_wait_read<1>();   // the previous chunk's store has finished reading its slot
+            __syncwarp();
+            ptx::mbar_arrive_e(&ctl->res_empty[prev]);
           }
           prev = slot;
           if (++slot == kResSlots) { slot = 0; ph ^= 1; }
         }
       }
-      ptx::bulk_wait<0>();
+      if (ptx::elect_one()) ptx::bulk_wait<0>();
+      __syncwarp();
     }
   } else if (warp >= kEpiWarp0) {
     // ----------------------------------------------------------------- epilogue
@@ -1024,10 +1028,10 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   const int threads = 64 + 32 * ew + (te ? 64 : 0);
   const int staging = te ? kResSlots * kResSlotBytes : ts ? ew * (ew == 16 ? 1 : 2) * 2048 : ew * 2048;
   const int slots = kp.pair ? max_pairs(reinterpret_cast<const void*>(fn), 200 * 1024, threads) : num_sms();
-  if (kp.b_resident && (num_kb * b_bytes > (kp.pair ? kResidentMaxPair : kResidentMax) || kp.num_n_tiles > slots)) kp.b_resident = 0;
+  if (kp.b_resident && (num_kb * b_bytes > (kp.pair ? kResidentMaxPair : kp.halo ? kHaloResidentMax : kResidentMax) || kp.num_n_tiles > slots)) kp.b_resident = 0;
   const int res_bytes = kp.b_resident ? num_kb * b_bytes : 0;
   if (kp.halo && !kp.b_resident) { set_error("conv: halo mode needs resident weights"); return cudaErrorInvalidValue; }
-  const int stage_bytes = kp.halo ? kHaloBytes : kp.b_resident ? a_bytes : a_bytes + b_bytes;
+  const int stage_bytes = kp.halo ? kHaloPixels * row_bytes : kp.b_resident ? a_bytes : a_bytes + b_bytes;
   kp.stages = std::max(2, std::min(kMaxStages, (kSmemBudget - static_cast<int>(sizeof(SmemCtl)) - staging - 1024 - res_bytes) / stage_bytes));
   const size_t smem = static_cast<size_t>(res_bytes) + static_cast<size_t>(kp.stages) * stage_bytes + sizeof(SmemCtl) + staging + 1024;
   int grid;  // in scheduling slots: CTAs, or CTA pairs
@@ -1127,8 +1131,8 @@ cudaError_t conv_forward(const ConvProblem& c, const Epilogue& e, cudaStream_t s
     const int cout_pad = ((c.Cout + 15) / 16) * 16;
     const long long w_bytes = static_cast<long long>(cout_pad) * c.taps * ctot * 2;
     const bool pair_ok = c.pair != 0 && (cout_pad / 2) % 8 == 0 && e.out_type != OUT_CLS_TAIL;
-    const bool fits = w_bytes <= kResidentMax || (pair_ok && w_bytes / 2 <= kResidentMaxPair);
-    kp.halo = (halo_env != 0 && c.taps == 9 && c.dil == 1 && c.nsrc == 1 && kp.BK == 64 && ctot <= 128 && cout_pad <= 256 &&
+    const bool fits = w_bytes <= kHaloResidentMax || (pair_ok && w_bytes / 2 <= kResidentMaxPair);
+    kp.halo = (halo_env != 0 && c.taps == 9 && c.dil == 1 && c.nsrc == 1 && ctot <= (kp.BK == 64 ? 128 : 32) && cout_pad <= 256 &&
                c.Cout % 16 == 0 && c.BN == 0 && c.resident != 0 && fits && c.W >= 8 && c.H >= 16)
                   ? 1 : 0;
   }
@@ -1151,7 +1155,9 @@ cudaError_t conv_forward(const ConvProblem& c, const Epilogue& e, cudaStream_t s
       kp.b_resident = 1;
       const long long w_bytes = static_cast<long long>(c.Cout) * c.taps * ctot * 2;
       const bool pair_ok = c.pair != 0 && (c.Cout / 2) % 8 == 0 && e.out_type != OUT_CLS_TAIL;
-      kp.pair = (w_bytes > kResidentMax || (pair_ok && pl.pair)) && pair_ok ? 1 : 0;
+      // a cta_group::2 MMA takes >= ~110 cycles whatever its N (measured), so narrow layers only pair up when
+      // the weights do not fit one CTA
+      kp.pair = (w_bytes > kHaloResidentMax && pair_ok) ? 1 : 0;
     }
   }
   kp.num_n_tiles = (c.Cout + kp.BN - 1) / kp.BN;

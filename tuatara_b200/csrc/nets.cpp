@@ -204,7 +204,7 @@ cudaError_t DeviceCtx::craft_forward(const uint8_t* in, int B, int H, int W, flo
     ConvProblem c;
     c.batch = B; c.H = H2; c.W = W2;
     c.src[0] = ConvSrc{k2, 32, 32};
-    c.taps = 9; c.dil = 1; c.Cout = 16; c.BN = 16;
+    c.taps = 9; c.dil = 1; c.Cout = 16;
     c.weight = w->craft.bf("cls3.w");
     Epilogue e;
     e.bias = w->craft.f32("cls3.b");

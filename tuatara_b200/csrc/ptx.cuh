@@ -52,14 +52,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> launch error the host reports) instead of hanging
-// the GPU.  The bound (2^22 polls, each a HW-suspended try_wait) is seconds, far above any
-// legitimate wait in these kernels.
+// Bounded wait: a protocol bug traps (-> launch error the host reports) instead of hanging the GPU.  The bound
+// is wall time (%globaltimer): 4 s, orders of magnitude above any legitimate wait in these kernels.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
 #pragma unroll 1
-  for (uint32_t i = 0; i < (1u << 22); ++i)
-    if (mbar_try_wait(bar, parity)) return;
-  __trap();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i)
+      if (mbar_try_wait(bar, parity)) return;
+    if (globaltimer_ns() - t0 > 4000000000ull) __trap();
+  }
 }
 
 // ----------------------------------------------------------------------- TMA
@@ -116,6 +125,76 @@ template <int N>
 __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (TMA store, tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------- warp-uniform issue ("_e": elect one lane inside the wrapper)
+// tcgen05.mma / commit / TMA take their operands from UNIFORM registers.  Issued from a `lane == 0` branch the
+// operands live in vector registers of divergent code, and ptxas wraps every instruction in a scalarisation loop
+// (ELECT + R2UR x4 + BRA.U.ANY): ~150 cycles per MMA whatever its N (measured, profiles/r1c_mma_issue.md).  With
+// the whole warp converged and one lane elected inside the asm block, descriptors stay in uniform registers.
+// elect.sync picks the same lane for the same mask every time, so commit / bulk-group tracking stays per thread.
+#define TT_ELECT_PRED "elect.sync _|q, 0xffffffff;\n\t"
+__device__ __forceinline__ void mbar_arrive_expect_tx_e(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .pred q;\n\t" TT_ELECT_PRED "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(
+                   smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_e(uint64_t* bar) {
+  asm volatile("{\n\t.reg .pred q;\n\t" TT_ELECT_PRED "@q mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_e(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile("{\n\t.reg .pred q;\n\t" TT_ELECT_PRED
+               "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(
+                   smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_e(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("{\n\t.reg .pred q;\n\t" TT_ELECT_PRED
+               "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}" ::"r"(
+                   smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_e(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile("{\n\t.reg .pred q;\n\t" TT_ELECT_PRED
+               "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(
+                   smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair_e(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile("{\n\t.reg .pred q;\n\t" TT_ELECT_PRED
+               "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}" ::"r"(
+                   smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_e(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("{\n\t.reg .pred q;\n\t" TT_ELECT_PRED
+               "@q cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n\t}" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_e() {
+  asm volatile("{\n\t.reg .pred q;\n\t" TT_ELECT_PRED "@q cp.async.bulk.commit_group;\n\t}" ::: "memory");
+}
+// wait_group is not predicable in one asm block without a branch: the elected lane waits, the others fall through
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred q;\n\t" TT_ELECT_PRED "selp.u32 %0, 1, 0, q;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mma_bf16_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p, q;\n\t" TT_ELECT_PRED
+               "setp.ne.b32 p, %4, 0;\n\t"
+               "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
+               "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_pair_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p, q;\n\t" TT_ELECT_PRED
+               "setp.ne.b32 p, %4, 0;\n\t"
+               "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc),
+               "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit_e(uint64_t* bar) {
+  asm volatile("{\n\t.reg .pred q;\n\t" TT_ELECT_PRED
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair_e(uint64_t* bar, uint16_t mask) {
+  asm volatile("{\n\t.reg .pred q;\n\t" TT_ELECT_PRED
+               "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+                   smem_u32(bar)), "h"(mask) : "memory");
+}
 
 // ------------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -275,19 +354,18 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t row_
   d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : 4) << 61; // swizzle mode
   return d;
 }
-// Same for a SWIZZLE_128B K-major tile whose 8-row groups are `sbo_bytes` apart.  Used by the halo convolution:
+// Same for a SWIZZLE_128B / SWIZZLE_64B K-major tile whose 8-row groups are `sbo_bytes` apart.  Used by the halo convolution:
 // a tap's A operand is the staged (TH+2) x 16-pixel tile read at a pixel offset, so the start address is NOT
 // 1024-byte aligned.  Measured on B200 (tests/test_gemm_gpu.py::test_conv_halo): the tensor core applies the
 // 128B-swizzle XOR to the absolute smem address bits, exactly as TMA wrote the tile, and the descriptor's
 // matrix-base-offset field (bits [49,52)) must stay 0 -- setting it to the row offset gives wrong products.
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
+__device__ __forceinline__ uint64_t make_smem_desc_sbo(uint32_t saddr, uint32_t row_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
   d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(base_off & 7) << 49;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(row_bytes == 128 ? 2 : 4) << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accum, bf16 A/B, both K-major.
