@@ -405,7 +405,7 @@ def run_native(args, rank, local_rank, world):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "configs[4]: synthetic 1280x1280 pages end-to-end, 300 words/page, reference defaults "
                                "(canvas 1024), CRAFT output overridden by the page's synthetic score map after CRAFT ran",
-                   "pages_per_gpu_per_step": n, "craft_batch_pages": args.batch_pages, "crops_per_page": WORDS,
+                   "pages_per_gpu_per_step": n, "group_pages": args.batch_pages, "craft_batch_pages": min(8, args.batch_pages), "crops_per_page": WORDS,
                    "weights": "seeded random init (CRAFT VGG16-BN, PARSeq-base)", "parallelism": f"dp{world} (pages)",
                    "kernel_paths": "conservative (retry after a failed first attempt)" if os.environ.get("TT_BENCH_RETRY") else "default",
                    "l2": f"inputs larger than L2: {n * PAGE * PAGE * 3 / 2**20:.0f} MiB of distinct pages per step"},
@@ -479,7 +479,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--pages-per-gpu", type=int, default=64)
-    ap.add_argument("--batch-pages", type=int, default=8)
+    ap.add_argument("--batch-pages", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

@@ -45,7 +45,7 @@ typedef struct tt_config {
   float link_threshold; /* 0.4   tuatara.cpp:398 */
   float low_text;       /* 0.4   tuatara.cpp:399 */
   int min_area;         /* 10    tuatara.cpp:148 */
-  int max_batch_pages;  /* pages processed per CRAFT batch per GPU (0 = default 8) */
+  int max_batch_pages;  /* pages per group = one PARSeq batch (0 = default 32); CRAFT runs in sub-batches of 8 inside it */
   int slots_per_gpu;    /* concurrent execution slots (streams + host threads) per GPU: 0 = default 2, max 4 */
 } tt_config;
 

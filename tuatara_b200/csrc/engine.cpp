@@ -21,7 +21,8 @@ namespace {
 
 constexpr int kCompCap = 2048;   // compact per-page result block: components
 constexpr int kRowCap = 32768;   //                                row extents
-constexpr int kMaxCropsPerPass = 4096;
+constexpr int kMaxCropsPerPass = 16384;
+constexpr int kCraftSubBatch = 8;   // pages per CRAFT / post-processing pass inside a group
 
 #define E_TRY(expr)                                   \
   do {                                                \
@@ -61,10 +62,12 @@ int detect_boxes(DeviceCtx& d, const tt_config& cfg, const float* maps_dev, int 
     PostParams pp;
     pp.low_text = cfg.low_text;
     pp.link_threshold = cfg.link_threshold;
-    E_TRY(post_run(ws, maps_dev, pp, d.stream));
     const size_t bytes = ws.result_stride * batch;
     E_TRY(d.ensure_pinned(bytes));
+    stage_begin(d.stream);
+    E_TRY(post_run(ws, maps_dev, pp, d.stream));
     E_CUDA(cudaMemcpyAsync(d.pinned, ws.result, bytes, cudaMemcpyDeviceToHost, d.stream));
+    stage_end(d.stream, "postprocess", 0.0, 24.0 * batch * H * W);  // 24 B per map pixel; kernels + the result D2H
     E_CUDA(cudaStreamSynchronize(d.stream));
     g_d2h_bytes += bytes;
     out->assign(batch, {});
@@ -79,60 +82,68 @@ int detect_boxes(DeviceCtx& d, const tt_config& cfg, const float* maps_dev, int 
   return 1;
 }
 
-// One group of equally sized pages on one device.
+// One group of equally sized pages on one device.  CRAFT + post-processing run in sub-batches of kCraftSubBatch
+// pages (its activations stay L2-friendlier: bigger batches ran 10 % slower per page), PARSeq runs once over the
+// crops of the whole group (its 27 decoder passes are launch-latency bound: their cost per page falls with the batch).
 int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const std::vector<int>& idx,
               const tt_ocr_options& opt, std::vector<PageOut>* results) {
   const cudaMemcpyKind page_kind = opt.pages_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   const int B = static_cast<int>(idx.size());
+  const int SB = std::min(B, kCraftSubBatch);
   const tt_image& first = pages[idx[0]];
   int th, tw, h32, w32;
   float ratio;
   resize_plan(first.rows, first.cols, cfg.canvas_size, cfg.mag_ratio, &th, &tw, &h32, &w32, &ratio);
   const size_t page_bytes = static_cast<size_t>(first.rows) * first.cols * 3;
   const size_t in_bytes = static_cast<size_t>(h32) * w32 * 3;
-  const size_t need = d.craft_bytes(B, h32, w32) + B * (page_bytes + in_bytes + 4096) + (8u << 20);
+  const size_t page_stride = (page_bytes + 255) & ~size_t(255);
+  const size_t need = d.craft_bytes(SB, h32, w32) + B * (page_stride + 4096) + SB * in_bytes + (8u << 20);
   E_TRY(d.arena.reserve(need));
   d.arena.reset();
-  uint8_t* pages_dev = d.arena.get<uint8_t>(B * ((page_bytes + 255) & ~size_t(255)));
-  uint8_t* craft_in = d.arena.get<uint8_t>(B * in_bytes);
-  if (!pages_dev || !craft_in) { set_error("arena exhausted (pages)"); return 1; }
-  const size_t page_stride = (page_bytes + 255) & ~size_t(255);
+  uint8_t* pages_dev = d.arena.get<uint8_t>(B * page_stride);
+  if (!pages_dev) { set_error("arena exhausted (pages)"); return 1; }
+  const size_t mark = d.arena.offset();
   std::vector<PageRef> refs(B);
-  stage_begin(d.stream);
-  for (int b = 0; b < B; ++b) {
-    const tt_image& im = pages[idx[b]];
-    uint8_t* dst = pages_dev + b * page_stride;
-    if (opt.pages_on_device) {
-      refs[b] = PageRef{im.data, im.rows, im.cols, im.step};  // already resident: read in place
-    } else {
-      E_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(im.cols) * 3, im.data, im.step,
-                               static_cast<size_t>(im.cols) * 3, im.rows, page_kind, d.stream));
-      g_h2d_bytes += page_bytes;
-      refs[b] = PageRef{dst, im.rows, im.cols, static_cast<size_t>(im.cols) * 3};
-    }
-    E_TRY(page_resize_pad(refs[b].data, im.rows, im.cols, refs[b].step, craft_in + b * in_bytes, th, tw, h32, w32,
-                          d.stream));
-  }
-  stage_end(d.stream, "preprocess", 0.0, static_cast<double>(B) * (page_bytes + in_bytes));
-  float* maps = nullptr;
-  stage_begin(d.stream);
-  E_TRY(d.craft_forward(craft_in, B, h32, w32, &maps));
-  // 27 convolutions of CRAFT: 711.4 FLOP per input pixel (= 746.0 GFLOP at 1024 x 1024)
-  stage_end(d.stream, "craft", 746.0e9 / (1024.0 * 1024.0) * B * h32 * w32, 0.0);
-  if (opt.score_override) {
-    const size_t map_elems = static_cast<size_t>(h32 / 2) * (w32 / 2) * 2;
-    for (int b = 0; b < B; ++b)
-      if (opt.score_override[idx[b]])
-      {
-        E_CUDA(cudaMemcpyAsync(maps + b * map_elems, opt.score_override[idx[b]], map_elems * sizeof(float),
-                               opt.override_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d.stream));
-        if (!opt.override_on_device) g_h2d_bytes += map_elems * sizeof(float);
+  std::vector<std::vector<DetBox>> det(B);
+  for (int s0 = 0; s0 < B; s0 += SB) {
+    const int nb = std::min(SB, B - s0);
+    d.arena.reset_to(mark);
+    uint8_t* craft_in = d.arena.get<uint8_t>(nb * in_bytes);
+    if (!craft_in) { set_error("arena exhausted (CRAFT input)"); return 1; }
+    stage_begin(d.stream);
+    for (int b = 0; b < nb; ++b) {
+      const tt_image& im = pages[idx[s0 + b]];
+      uint8_t* dst = pages_dev + (s0 + b) * page_stride;
+      if (opt.pages_on_device) {
+        refs[s0 + b] = PageRef{im.data, im.rows, im.cols, im.step};  // already resident: read in place
+      } else {
+        E_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(im.cols) * 3, im.data, im.step,
+                                 static_cast<size_t>(im.cols) * 3, im.rows, page_kind, d.stream));
+        g_h2d_bytes += page_bytes;
+        refs[s0 + b] = PageRef{dst, im.rows, im.cols, static_cast<size_t>(im.cols) * 3};
       }
+      E_TRY(page_resize_pad(refs[s0 + b].data, im.rows, im.cols, refs[s0 + b].step, craft_in + b * in_bytes, th, tw, h32, w32,
+                            d.stream));
+    }
+    stage_end(d.stream, "preprocess", 0.0, static_cast<double>(nb) * (page_bytes + in_bytes));
+    float* maps = nullptr;
+    stage_begin(d.stream);
+    E_TRY(d.craft_forward(craft_in, nb, h32, w32, &maps));
+    // 27 convolutions of CRAFT: 711.4 FLOP per input pixel (= 746.0 GFLOP at 1024 x 1024)
+    stage_end(d.stream, "craft", 746.0e9 / (1024.0 * 1024.0) * nb * h32 * w32, 0.0);
+    if (opt.score_override) {
+      const size_t map_elems = static_cast<size_t>(h32 / 2) * (w32 / 2) * 2;
+      for (int b = 0; b < nb; ++b)
+        if (opt.score_override[idx[s0 + b]]) {
+          E_CUDA(cudaMemcpyAsync(maps + b * map_elems, opt.score_override[idx[s0 + b]], map_elems * sizeof(float),
+                                 opt.override_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d.stream));
+          if (!opt.override_on_device) g_h2d_bytes += map_elems * sizeof(float);
+        }
+    }
+    std::vector<std::vector<DetBox>> sub;
+    if (detect_boxes(d, cfg, maps, nb, h32 / 2, w32 / 2, &sub)) return 1;
+    for (int b = 0; b < nb; ++b) det[s0 + b] = std::move(sub[b]);
   }
-  std::vector<std::vector<DetBox>> det;
-  stage_begin(d.stream);
-  if (detect_boxes(d, cfg, maps, B, h32 / 2, w32 / 2, &det)) return 1;
-  stage_end(d.stream, "postprocess", 0.0, 24.0 * B * (h32 / 2) * (w32 / 2));  // 24 B per map pixel
 
   // host: rescale boxes, bounding rects, output bboxes (tuatara.cpp:406-418, :256-274)
   const float inv = 1.f / ratio;  // ratio_w == ratio_h (tuatara.cpp:360-361)
@@ -159,8 +170,8 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
   std::vector<int> all_ids(static_cast<size_t>(n) * d.w->pd.L);
   for (int c0 = 0; c0 < n; c0 += kMaxCropsPerPass) {
     const int nc = std::min(kMaxCropsPerPass, n - c0);
-    // recycle: keep [pages_dev, craft_in) region by re-reserving on top of it
-    const size_t keep = B * page_stride + B * in_bytes + 8192;
+    // recycle: keep the page buffers by re-reserving on top of them
+    const size_t keep = B * page_stride + 8192;
     const size_t need2 = keep + d.parseq_bytes(nc) + static_cast<size_t>(nc) * (128 * 96 * 2 + sizeof(CropBox)) +
                          B * sizeof(PageRef) + (4u << 20);
     if (need2 > d.arena.capacity()) {
@@ -168,7 +179,6 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
       E_TRY(d.arena.reserve(need2));
       d.arena.reset();
       pages_dev = d.arena.get<uint8_t>(B * page_stride);
-      craft_in = d.arena.get<uint8_t>(B * in_bytes);
       for (int b = 0; b < B; ++b) {
         const tt_image& im = pages[idx[b]];
         uint8_t* dst = pages_dev + b * page_stride;
@@ -178,9 +188,7 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
         refs[b].data = dst;
       }
     } else {
-      d.arena.reset();
-      d.arena.get<uint8_t>(B * page_stride);
-      d.arena.get<uint8_t>(B * in_bytes);
+      d.arena.reset_to(mark);
     }
     PageRef* refs_dev = d.arena.get<PageRef>(B);
     CropBox* boxes_dev = d.arena.get<CropBox>(nc);
@@ -219,7 +227,7 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
 int run_device(tt_engine& e, int g, const tt_image* pages, const std::vector<int>& mine, const tt_ocr_options& opt,
                std::vector<PageOut>* results, std::string* err) {
   const tt_config& cfg = e.cfg;
-  const int max_b = cfg.max_batch_pages > 0 ? cfg.max_batch_pages : 8;
+  const int max_b = cfg.max_batch_pages > 0 ? cfg.max_batch_pages : 32;
   std::vector<std::vector<int>> groups;
   size_t i = 0;
   while (i < mine.size()) {

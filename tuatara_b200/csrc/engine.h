@@ -44,6 +44,8 @@ class Arena {
   ~Arena();
   cudaError_t reserve(size_t bytes);
   void reset() { off_ = 0; }
+  size_t offset() const { return off_; }
+  void reset_to(size_t off) { off_ = off; }  // drop everything allocated after a mark taken with offset()
   void* alloc(size_t bytes);  // nullptr when exhausted (caller reserved too little)
   template <class T> T* get(size_t n) { return static_cast<T*>(alloc(n * sizeof(T))); }
   size_t capacity() const { return cap_; }

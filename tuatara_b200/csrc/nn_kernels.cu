@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtens
   uint8_t* sP = smem;  // aliases Q|K
   AttnCtl* ctl = reinterpret_cast<AttnCtl*>(smem + 49152);
   const int head = blockIdx.x, crop = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform: warp 0 issues through the uniform datapath
 
   if (tid == 0) {
     ptx::prefetch_tmap(&tm_qkv);
@@ -188,22 +188,23 @@ __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtens
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem = ctl->tmem_base;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
 
-  if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(&ctl->bar_load, 3 * 16384);
-    ptx::tma_load_2d(sQ, &tm_qkv, &ctl->bar_load, head * 64, crop * 128);
-    ptx::tma_load_2d(sK, &tm_qkv, &ctl->bar_load, D + head * 64, crop * 128);
-    ptx::tma_load_2d(sV, &tm_qkv, &ctl->bar_load, 2 * D + head * 64, crop * 128);
+  if (warp == 0) {  // all 32 lanes converged, one elected lane issues (ptx.cuh "_e" wrappers)
+    ptx::mbar_arrive_expect_tx_e(&ctl->bar_load, 3 * 16384);
+    ptx::tma_load_2d_e(sQ, &tm_qkv, &ctl->bar_load, head * 64, crop * 128);
+    ptx::tma_load_2d_e(sK, &tm_qkv, &ctl->bar_load, D + head * 64, crop * 128);
+    ptx::tma_load_2d_e(sV, &tm_qkv, &ctl->bar_load, 2 * D + head * 64, crop * 128);
     ptx::mbar_wait(&ctl->bar_load, 0);
+    __syncwarp();
     ptx::tc_fence_after();
     // S[128 q][128 k] = Q K^T : both operands K-major over the 64 head dims
     const uint32_t idesc = ptx::make_idesc_bf16(128, 128);
     const uint32_t qa = ptx::smem_u32(sQ), ka = ptx::smem_u32(sK);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      ptx::mma_bf16(tmem, ptx::make_smem_desc(qa + k * 32, 128), ptx::make_smem_desc(ka + k * 32, 128), idesc, k != 0);
-    ptx::mma_commit(&ctl->bar_s);
+      ptx::mma_bf16_e(tmem, ptx::make_smem_desc(qa + k * 32, 128), ptx::make_smem_desc(ka + k * 32, 128), idesc, k != 0);
+    ptx::mma_commit_e(&ctl->bar_s);
   }
   ptx::mbar_wait(&ctl->bar_s, 0);
   ptx::tc_fence_after();
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtens
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   ptx::tc_fence_before();
   __syncthreads();
-  if (tid == 0) {
+  if (warp == 0) {
     ptx::tc_fence_after();
     // O[128 q][64 d] = P V : A = P (K-major over keys), B = V as loaded: rows = keys, 64 dims contiguous
     // == MN-major SWIZZLE_128B, one 1024-byte atom per 8 keys (SBO = 1024), 16 keys per MMA.
@@ -261,9 +262,9 @@ __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtens
     for (int k = 0; k < 8; ++k) {
       const uint64_t da = ptx::make_smem_desc(pa + (k >> 2) * 16384 + (k & 3) * 32, 128);
       const uint64_t db = ptx::make_smem_desc(va + k * 2048, 128);
-      ptx::mma_bf16(tmem, da, db, idesc, k != 0);
+      ptx::mma_bf16_e(tmem, da, db, idesc, k != 0);
     }
-    ptx::mma_commit(&ctl->bar_o);
+    ptx::mma_commit_e(&ctl->bar_o);
   }
   ptx::mbar_wait(&ctl->bar_o, 0);
   ptx::tc_fence_after();
