@@ -63,7 +63,7 @@ def measured_peaks():
 
 def gemm_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), else None."""
-    p = ROOT / "profiles" / "r1_gemm_traffic.json"
+    p = ROOT / "profiles" / "gemm_traffic.json"
     return json.loads(p.read_text())["dram_bytes_per_launch"] if p.exists() else None
 
 

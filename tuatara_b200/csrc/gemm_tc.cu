@@ -131,7 +131,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 
 // Packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2): one issue slot per two elements.  With two epilogue warps
 // per scheduler the epilogue, not the tensor pipe, set the pace of the K=384 GEMMs (ncu: 14.5 warp instructions
-// per output element, issue slots 50 % busy, tensor pipe 37 %; profiles/r1b_gemm_fc1.md).
+// per output element, issue slots 50 % busy, tensor pipe 37 %; profiles/r1b_gemm_roles.md).
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
   uint64_t r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -181,7 +181,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // OUT: OUT_BF16 / OUT_F32 / OUT_CLS_TAIL; ACT: ACT_*; RES: fp32 residual added (OUT_F32 only).  The epilogue is
 // specialised at compile time: with these as runtime flags only ~1/4 of its executed instructions were
-// useful work (ncu opcode histogram, profiles/r1_gemm_epilogue.md) and it, not the MMA, set the pace.
+// useful work (ncu opcode histogram, profiles/r1b_gemm_roles.md) and it, not the MMA, set the pace.
 // TE ("TMA epilogue", fp32 output + fp32 residual only): warp 2 streams the residual tile through a smem ring with
 // TMA loads that run ahead of the MMAs (the register path had one 2 KB segment per warp in flight and the
 // epilogue took 2.6x the mainloop: profiles/r1b_gemm_roles.md), 4 epilogue warps add accumulator + bias to their

@@ -129,7 +129,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // ------------------------------------------------- warp-uniform issue ("_e": elect one lane inside the wrapper)
 // tcgen05.mma / commit / TMA take their operands from UNIFORM registers.  Issued from a `lane == 0` branch the
 // operands live in vector registers of divergent code, and ptxas wraps every instruction in a scalarisation loop
-// (ELECT + R2UR x4 + BRA.U.ANY): ~150 cycles per MMA whatever its N (measured, profiles/r1c_mma_issue.md).  With
+// (ELECT + R2UR x4 + BRA.U.ANY): ~150 cycles per MMA whatever its N (measured, profiles/r1b_gemm_roles.md section 3).  With
 // the whole warp converged and one lane elected inside the asm block, descriptors stay in uniform registers.
 // elect.sync picks the same lane for the same mask every time, so commit / bulk-group tracking stays per thread.
 #define TT_ELECT_PRED "elect.sync _|q, 0xffffffff;\n\t"
