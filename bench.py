@@ -464,9 +464,10 @@ def supervise(args) -> bool:
             print(f"bench.py: child exceeded {budget} s, retrying", file=sys.stderr, flush=True)
             continue
         text = out.decode(errors="replace")
-        if p.returncode == 0 and (env_int("RANK", 0) != 0 or '"metric"' in text):
-            sys.stdout.write(text)
-            sys.stdout.flush()
+        lines = [ln for ln in text.splitlines() if ln.startswith("{")]  # only the JSON line (NCCL prints its version to stdout)
+        if p.returncode == 0 and (env_int("RANK", 0) != 0 or lines):
+            for ln in lines:
+                print(ln, flush=True)
             return True
         print(f"bench.py: child failed (rc {p.returncode}), retrying", file=sys.stderr, flush=True)
     raise SystemExit("bench.py: native arm failed twice")
