@@ -74,7 +74,7 @@ def normalise_maps(textmap: torch.Tensor, linkmap: torch.Tensor):
 
 
 def get_detected_boxes(textmap: torch.Tensor, linkmap: torch.Tensor, text_threshold: float,
-                       link_threshold: float, low_text: float, keep_points: bool = False):
+                       link_threshold: float, low_text: float, keep_points: bool = False, min_area: int = 10):
     """tuatara.cpp:119-204.  Returns (list of RotatedRect tuples ((cx,cy),(w,h),angle), DetDebug).
     The dead 'diamond'/start-corner code at :180-198 only mutates a local and is omitted."""
     tn, ln = normalise_maps(textmap.contiguous().float(), linkmap.contiguous().float())
@@ -91,7 +91,7 @@ def get_detected_boxes(textmap: torch.Tensor, linkmap: torch.Tensor, text_thresh
     link_only = (link_score == 1) & (text_score == 0)  # :160
     for k in range(1, n_labels):  # :146
         size = int(stats[k, cv2.CC_STAT_AREA])
-        if size < 10:  # :147-148
+        if size < min_area:  # :147-148 (literal 10)
             continue
         mask = labels == k  # :150
         max_val = float(textmap_cv[mask].max())  # :151-152 minMaxLoc with mask
@@ -230,16 +230,19 @@ def run_parseq(parseq_model, crops_u8: np.ndarray, chunk_size: int = 4) -> torch
 
 
 def image_to_data(image: np.ndarray, craft_model, parseq_model, score_override=None,
-                  chunk_size: int = 4, stages: Stages | None = None):
+                  chunk_size: int = 4, stages: Stages | None = None, canvas_size: int = 1024, mag_ratio: float = 1.0,
+                  text_threshold: float = 0.7, link_threshold: float = 0.4, low_text: float = 0.4, min_area: int = 10):
     """tuatara.cpp:314-512 with models passed in (the reference reloads them per call).
 
     ``image``: uint8 (H,W,3) exactly as the caller's buffer (BGR from cv::imread, RGB from
     bindings/run_ocr.py).  ``score_override``: optional (score_text, score_link) fp32 arrays
     that replace CRAFT's output (CRAFT still runs) -- needed because random-init weights give
-    one giant component.  Returns list of dict(text=..., bbox=[4 floats])."""
+    one giant component (SURVEY 8d).  The keyword defaults are the reference's literals (:352-353, :397-399, :148);
+    passing others is the config struct its TODO at :396 asks for.
+    Returns list of dict(text=..., bbox=[4 floats])."""
     st = stages if stages is not None else Stages()
     image = cv2.cvtColor(image, cv2.COLOR_BGR2RGB)  # :349 (in place in C++; swaps ch 0<->2)
-    image_resized, target_ratio, _ = resize_aspect_ratio(image, 1024, cv2.INTER_LINEAR, 1.0)  # :352-358
+    image_resized, target_ratio, _ = resize_aspect_ratio(image, canvas_size, cv2.INTER_LINEAR, mag_ratio)  # :352-358
     ratio_h = f32(1) / target_ratio  # :360
     ratio_w = f32(1) / target_ratio  # :361
     st.craft_input_u8, st.ratio = image_resized, float(target_ratio)
@@ -252,7 +255,8 @@ def image_to_data(image: np.ndarray, craft_model, parseq_model, score_override=N
         score_text = torch.from_numpy(np.ascontiguousarray(score_override[0]))
         score_link = torch.from_numpy(np.ascontiguousarray(score_override[1]))
     st.score_text, st.score_link = score_text.numpy().copy(), score_link.numpy().copy()
-    det, st.det_debug = get_detected_boxes(score_text, score_link, 0.7, 0.4, 0.4)  # :397-400
+    det, st.det_debug = get_detected_boxes(score_text, score_link, text_threshold, link_threshold, low_text,
+                                           min_area=min_area)  # :397-400
     boxes = adjust_result_coordinates(det, ratio_w, ratio_h)  # :406
     st.det, st.boxes = det, boxes
     if not boxes:  # the reference crashes in torch::cat({}) (:485); we return {}

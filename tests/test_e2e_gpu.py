@@ -48,3 +48,27 @@ def test_mixed_sizes_and_empty(engine):
     b = np.full((300, 500, 3), 255, np.uint8)
     out = engine.ocr_pages([a, b, a[:700]])
     assert len(out) == 3
+
+
+def test_config_struct_native_canvas_and_thresholds(weights_dir, oracle_models):
+    """tt_config (the reference's TODO at tuatara.cpp:396): a native-resolution canvas (1280 -> CRAFT input 1280^2,
+    maps 640^2) and non-default thresholds / min_area give the oracle's boxes when it is run with the same values."""
+    import cv2
+
+    craft, _ = oracle_models
+    cfg = tb.default_config()
+    cfg.canvas_size, cfg.text_threshold, cfg.link_threshold, cfg.low_text, cfg.min_area = 1280.0, 0.6, 0.3, 0.35, 40
+    eng = tb.Engine(weights_dir, cfg=cfg)
+    try:
+        page = synth.synth_page(7)
+        m512 = synth.synth_score_maps(7)
+        m640 = np.ascontiguousarray(cv2.resize(m512, (640, 640), interpolation=cv2.INTER_LINEAR))  # maps of the 1280 canvas
+        got = eng.ocr_pages([page], score_override=[m640])[0]
+        dummy_parseq = lambda x: torch.zeros(x.shape[0], 26, 95)  # noqa: E731
+        ref = R.image_to_data(page.copy(), craft, dummy_parseq, score_override=(m640[..., 0], m640[..., 1]), canvas_size=1280,
+                              text_threshold=0.6, link_threshold=0.3, low_text=0.35, min_area=40)
+        ref_default = R.image_to_data(page.copy(), craft, dummy_parseq, score_override=(m512[..., 0], m512[..., 1]))
+        assert len(ref) > 0 and [g["bbox"] for g in got] == [r["bbox"] for r in ref]
+        assert [r["bbox"] for r in ref] != [r["bbox"] for r in ref_default]  # the settings do change the result
+    finally:
+        eng.close()
