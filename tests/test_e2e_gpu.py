@@ -72,3 +72,18 @@ def test_config_struct_native_canvas_and_thresholds(weights_dir, oracle_models):
         assert [r["bbox"] for r in ref] != [r["bbox"] for r in ref_default]  # the settings do change the result
     finally:
         eng.close()
+
+
+def test_two_gpu_engine_shards_pages(weights_dir):
+    """One engine over two devices: page i runs on device i mod 2, results gathered in page order."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    pages = [synth.synth_page(i) for i in range(5)]
+    maps = [synth.synth_score_maps(i) for i in range(5)]
+    one = tb.Engine(weights_dir, devices=[0])
+    two = tb.Engine(weights_dir, devices=[0, 1])
+    try:
+        assert two.ocr_pages(pages, score_override=maps) == one.ocr_pages(pages, score_override=maps)
+    finally:
+        one.close()
+        two.close()
