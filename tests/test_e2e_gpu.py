@@ -87,3 +87,15 @@ def test_two_gpu_engine_shards_pages(weights_dir):
     finally:
         one.close()
         two.close()
+
+
+def test_pages_are_independent_units_at_full_size(engine):
+    """configs[4] shape (1280x1280 pages, 300 words each, 2400 crops in one PARSeq batch): each page's items must be
+    the same whether it is processed alone or inside a group -- the property the data-parallel sharding rests on."""
+    pages = [synth.synth_page(i) for i in range(8)]
+    maps = [synth.synth_score_maps(i) for i in range(8)]
+    together = engine.ocr_pages(pages, score_override=maps)
+    assert [len(p) for p in together] == [300] * 8
+    for i in (0, 3, 7):
+        alone = engine.ocr_pages([pages[i]], score_override=[maps[i]])[0]
+        assert alone == together[i]

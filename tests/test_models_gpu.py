@@ -107,3 +107,17 @@ def test_decode_matches_reference_tokenizer(native_lib):
     ref = [R.truncate_at_eos(t) for t in tok.decode(torch.softmax(logits, -1))]
     ids = logits.argmax(-1).numpy().astype(np.int32)
     assert tb.decode_ids(ids) == ref
+
+
+def test_parseq_full_batch_is_batch_invariant(engine):
+    """configs[2] size (1024 synthetic 32x128 crops): a size-independent property instead of the oracle, which needs
+    minutes for this batch -- every crop's logits / ids must not depend on what else is in the batch (tile schedule,
+    CTA pairs, weight-resident vs streaming, TMA vs register epilogues all change with M; the arithmetic must not)."""
+    crops = np.random.default_rng(0).integers(0, 256, (1024, 32, 128, 3), dtype=np.uint8)
+    crops[:512] = _crops(342, seed=5)[:512]  # half page-like crops, half noise
+    logits, ids = engine.parseq_forward(crops)
+    assert np.isfinite(logits).all()
+    for s in range(0, 1024, 192):  # ragged sub-batches: 192, ..., 64
+        l2, i2 = engine.parseq_forward(crops[s:s + 192])
+        assert np.array_equal(i2, ids[s:s + 192])
+        assert float(np.abs(l2 - logits[s:s + 192]).max()) <= 1e-4
