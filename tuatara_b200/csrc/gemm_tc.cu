@@ -174,6 +174,9 @@ __device__ __forceinline__ uint64_t gelu_fast2(uint64_t x) {
   return fma2(hx, pk2(ta, tb), hx);
 }
 
+// role counters (TT_GEMM_DEBUG & 4) read the clock only when they are on
+__device__ __forceinline__ long long dbg_clock(bool on) { return on ? clock64() : 0; }
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -218,6 +221,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  const bool dbgt = (p.debug & 4) != 0;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&p.tmA[0]);
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
       int stage = 0;
       uint32_t phase = 0;
       long long dbg_prod_wait = 0;
-      const long long dbg_t_start = clock64();
+      const long long dbg_t_start = dbg_clock(dbgt);
       for (; it.valid(); it.next()) {
         const int n_tile = it.n_tile(p), m_tile = PAIR ? it.m_tile(p) * 2 + static_cast<int>(rank) : it.m_tile(p);
         int img = 0, y0 = 0, x0 = 0;
@@ -307,7 +311,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
           const int dx = (p.taps == 9) ? (tap % 3 - 1) * p.dil : 0;
           for (int src = 0; src < 2; ++src) {
             for (int cb = 0; cb < p.kb_src[src]; ++cb, ++kb) {
-              { const long long t0 = clock64(); ptx::mbar_wait(&ctl->empty[stage], phase ^ 1); __syncwarp(); dbg_prod_wait += clock64() - t0; }
+              { const long long t0 = dbg_clock(dbgt); ptx::mbar_wait(&ctl->empty[stage], phase ^ 1); __syncwarp(); dbg_prod_wait += dbg_clock(dbgt) - t0; }
               uint8_t* sA = ring + stage * stage_bytes;
               if (rank == 0) ptx::mbar_arrive_expect_tx_e(&ctl->full[stage], tx_mult * static_cast<uint32_t>(stage_bytes));
               if constexpr (PAIR) {
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
-      if ((p.debug & 4) && blockIdx.x == 0 && lane == 0) { p.dbg_out[0] = dbg_prod_wait; p.dbg_out[1] = clock64() - dbg_t_start; }
+      if ((p.debug & 4) && blockIdx.x == 0 && lane == 0) { p.dbg_out[0] = dbg_prod_wait; p.dbg_out[1] = dbg_clock(dbgt) - dbg_t_start; }
     }
   } else if (warp == 1) {
     // --------------------------------------------------------------- MMA issuer
@@ -351,14 +355,14 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
       if (resident && it.valid()) ptx::mbar_wait(&ctl->b_full, 0);
       const int ksteps = p.BK / 16;
       long long dbg_w_acc = 0, dbg_w_full = 0;
-      const long long dbg_t_start = clock64();
+      const long long dbg_t_start = dbg_clock(dbgt);
       for (; it.valid(); it.next()) {
-        { const long long t0 = clock64(); ptx::mbar_wait(&ctl->acc_empty[as], aphase ^ 1); dbg_w_acc += clock64() - t0; }
+        { const long long t0 = dbg_clock(dbgt); ptx::mbar_wait(&ctl->acc_empty[as], aphase ^ 1); dbg_w_acc += dbg_clock(dbgt) - t0; }
         __syncwarp(); ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * kAccStride;
         if (p.halo) {
           for (int cb = 0; cb < p.kb_src[0]; ++cb) {
-            { const long long t0 = clock64(); ptx::mbar_wait(&ctl->full[stage], phase); dbg_w_full += clock64() - t0; }
+            { const long long t0 = dbg_clock(dbgt); ptx::mbar_wait(&ctl->full[stage], phase); dbg_w_full += dbg_clock(dbgt) - t0; }
             __syncwarp(); ptx::tc_fence_after();
             const uint32_t h_addr = ptx::smem_u32(ring + stage * stage_bytes);
             for (int tap = 0; tap < 9; ++tap) {
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
           continue;
         }
         for (int kb = 0; kb < num_kb; ++kb) {
-          { const long long t0 = clock64(); ptx::mbar_wait(&ctl->full[stage], phase); dbg_w_full += clock64() - t0; }
+          { const long long t0 = dbg_clock(dbgt); ptx::mbar_wait(&ctl->full[stage], phase); dbg_w_full += dbg_clock(dbgt) - t0; }
           __syncwarp(); ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(ring + stage * stage_bytes);
           const uint32_t b_addr = resident ? ptx::smem_u32(sBres + kb * b_bytes) : a_addr + a_bytes;
@@ -400,7 +404,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
         else ptx::mma_commit_e(&ctl->acc_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
-      if ((p.debug & 4) && blockIdx.x == 0 && lane == 0) { p.dbg_out[2] = dbg_w_acc; p.dbg_out[3] = dbg_w_full; p.dbg_out[4] = clock64() - dbg_t_start; }
+      if ((p.debug & 4) && blockIdx.x == 0 && lane == 0) { p.dbg_out[2] = dbg_w_acc; p.dbg_out[3] = dbg_w_full; p.dbg_out[4] = dbg_clock(dbgt) - dbg_t_start; }
     }
   } else if (TE && warp == 2) {
     // ------------------------------------------------- residual loader (TMA epilogue)
@@ -533,8 +537,8 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
       if constexpr (TE) {
         // out = residual + (acc + bias), chunk by chunk: this thread's row of the chunk sits at r*128 in the slot,
         // its 16-byte units XOR-swizzled by (r & 7) (SWIZZLE_128B) -- the same layout the TMA store reads back.
-        { const long long t0 = clock64(); ptx::mbar_wait(&ctl->acc_full[as], aphase); dbg_e_wait += clock64() - t0; }
-        const long long dbg_t_busy0 = clock64();
+        { const long long t0 = dbg_clock(dbgt); ptx::mbar_wait(&ctl->acc_full[as], aphase); dbg_e_wait += dbg_clock(dbgt) - t0; }
+        const long long dbg_t_busy0 = dbg_clock(dbgt);
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
         const uint32_t bias_row = bias_s + as * 1024;
@@ -563,12 +567,12 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
           ptx::mbar_arrive(&ctl->chunk_done[te_slot]);
           if (++te_slot == kResSlots) { te_slot = 0; te_ph ^= 1; }
         }
-        dbg_e_busy += clock64() - dbg_t_busy0;
+        dbg_e_busy += dbg_clock(dbgt) - dbg_t_busy0;
       } else if constexpr (OUT == OUT_CLS_TAIL) {
         // BN == 16: v = relu(conv 32->16 + b); two 1x1 convs in registers; fp32 [pixel][2] store
         long long orow;
         const bool valid = row_to_out(m_tile, r, orow);
-        { const long long t0 = clock64(); ptx::mbar_wait(&ctl->acc_full[as], aphase); dbg_e_wait += clock64() - t0; }
+        { const long long t0 = dbg_clock(dbgt); ptx::mbar_wait(&ctl->acc_full[as], aphase); dbg_e_wait += dbg_clock(dbgt) - t0; }
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
         if (part == 0) {
@@ -643,8 +647,8 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
           }
         }
         (void)ts_c1; (void)ts_c2; (void)ts_c3;
-        { const long long t0 = clock64(); ptx::mbar_wait(&ctl->acc_full[as], aphase); dbg_e_wait += clock64() - t0; }
-        const long long dbg_t_busy0 = clock64();
+        { const long long t0 = dbg_clock(dbgt); ptx::mbar_wait(&ctl->acc_full[as], aphase); dbg_e_wait += dbg_clock(dbgt) - t0; }
+        const long long dbg_t_busy0 = dbg_clock(dbgt);
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
         const uint32_t bias_row = bias_s + as * 1024;
@@ -757,7 +761,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
             }
           }
         }
-        dbg_e_busy += clock64() - dbg_t_busy0;
+        dbg_e_busy += dbg_clock(dbgt) - dbg_t_busy0;
       }
       ptx::tc_fence_before();
       __syncwarp();
