@@ -672,7 +672,9 @@ cudaError_t maxpool3x3s1(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int
 }
 cudaError_t upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * 4 * H * W * (C / 8);
-  k_upsample2<<<grid_for(total, 256), 256, 0, s>>>(in, out, B, H, W, C);
+  // one element group per thread (no grid-stride tail): with 2368 blocks looping 23 times each the kernel sat at 24 % of
+  // the HBM peak waiting on its four dependent loads (profiles/r1c_other_kernels.md)
+  k_upsample2<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out, B, H, W, C);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }
