@@ -343,6 +343,12 @@ __global__ void k_dec_self_attn(DecoderStep st, const float* __restrict__ q_tabl
   }
   const int nkeys = st.refine ? L : p + 1;
   const bool mine = lane < nkeys && (st.refine ? (lane != p + 1 && lane < first_eos) : true);
+  // every V element this lane will need (dim = lane of keys 0..nkeys-1) is requested before the scores are computed:
+  // one memory round trip for the whole kernel instead of one per 8 keys
+  const __nv_bfloat16* vbase = kbase + D + lane;
+  __nv_bfloat16 vraw[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) vraw[j] = (j < nkeys) ? vbase[static_cast<long long>(j) * 2 * D] : __float2bfloat16(0.f);
   float score = -INFINITY;
   if (mine) {
     const float4* q4 = reinterpret_cast<const float4*>(q_table + p * D + head * 32);
@@ -364,14 +370,8 @@ __global__ void k_dec_self_attn(DecoderStep st, const float* __restrict__ q_tabl
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float pr = e / sum;
   float acc = 0.f;
-  const __nv_bfloat16* vbase = kbase + D + lane;
-  for (int j0 = 0; j0 < nkeys; j0 += 8) {
-    float vv[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) vv[u] = (j0 + u < nkeys) ? __bfloat162float(vbase[static_cast<long long>(j0 + u) * 2 * D]) : 0.f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) acc += __shfl_sync(0xffffffffu, pr, (j0 + u) & 31) * vv[u];
-  }
+  for (int j = 0; j < 32; ++j) acc += __shfl_sync(0xffffffffu, pr, j) * __bfloat162float(vraw[j]);  // pr == 0 beyond nkeys
   out[(static_cast<long long>(crop) * st.np + pi) * D + head * 32 + lane] = __float2bfloat16(acc);
 }
 
