@@ -31,3 +31,27 @@ for name, (h, w) in {"resume 763x607": (763, 607), "funsd 1000x754": (1000, 754)
         ts.append(time.perf_counter() - t0)
     print(f"{name}: {len(out[0])} items, median {np.median(ts) * 1e3:.2f} ms, min {min(ts) * 1e3:.2f} ms per page (1 page per call)")
 eng.close()
+
+# stage breakdown of the single-page call (CUDA-event intervals on the engine's stream)
+import ctypes as C  # noqa: E402
+lib = tb.lib()
+eng = tb.Engine(wdir, devices=[0])
+page, m = full, fmap
+for _ in range(3):
+    eng.ocr_pages([page], score_override=[m])
+lib.tt_profile_enable(1)
+N = 5
+t0 = time.perf_counter()
+for _ in range(N):
+    eng.ocr_pages([page], score_override=[m])
+wall = (time.perf_counter() - t0) / N
+lib.tt_profile_enable(0)
+buf = C.create_string_buffer(1 << 14)
+lib.tt_profile_stages(buf, len(buf))
+pm, pf, pl = C.c_double(), C.c_double(), C.c_ulonglong()
+lib.tt_profile_collect(C.byref(pm), C.byref(pf), C.byref(pl))
+print(f"single 1280x1280 page with profiling on: {wall * 1e3:.2f} ms wall; gemm launches {pl.value // N} taking {pm.value / N:.2f} ms")
+for ln in buf.value.decode().splitlines():
+    name, cnt, ms, fl, by = ln.split(",")
+    print(f"  {name:16s} {float(ms) / N:7.3f} ms")
+eng.close()
