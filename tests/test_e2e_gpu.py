@@ -99,3 +99,17 @@ def test_pages_are_independent_units_at_full_size(engine):
     for i in (0, 3, 7):
         alone = engine.ocr_pages([pages[i]], score_override=[maps[i]])[0]
         assert alone == together[i]
+
+
+def test_concurrent_callers_are_serialised_safely(engine):
+    """image_to_data is re-entrant in the reference (no globals); here concurrent callers of one engine share its
+    execution slots behind per-slot mutexes and must each get the single-caller result."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    pages = [np.ascontiguousarray(synth.synth_page(i)[:640, :768]) for i in range(4)]
+    maps = [np.ascontiguousarray(synth.synth_score_maps(i)[:320, :384]) for i in range(4)]
+    serial = [engine.ocr_pages([p], score_override=[m])[0] for p, m in zip(pages, maps)]
+    with ThreadPoolExecutor(4) as ex:
+        for _ in range(3):
+            got = list(ex.map(lambda pm: engine.ocr_pages([pm[0]], score_override=[pm[1]])[0], zip(pages, maps)))
+            assert got == serial
