@@ -119,15 +119,7 @@ struct TileIter {
 // the erf form: |error| <= 2.6e-5 on the real line (the textbook tanh form is off by 4.7e-4), plus
 // tanh.approx.f32's 2^-11 relative error -- both far below the bf16 rounding applied to the result.
 // 8 issue slots + 1 MUFU per element: the exact erf costs > 20 and made fc1's epilogue the bottleneck.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float x2 = fminf(x * x, 36.0f);  // tanh is saturated beyond |x| = 6; keeps the quartic monotone
-  float p = fmaf(x2, -0.00035151678866f, 0.037005646023f);
-  p = fmaf(x2, p, 0.797507884285f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
-}
+// (evaluated two elements at a time with packed fp32x2 arithmetic: gelu_fast2 below)
 
 // Packed fp32x2 arithmetic (sm_100 FFMA2/FMUL2/FADD2): one issue slot per two elements.  With two epilogue warps
 // per scheduler the epilogue, not the tensor pipe, set the pace of the K=384 GEMMs (ncu: 14.5 warp instructions
