@@ -442,13 +442,13 @@ def supervise(args) -> bool:
     """Runs the native arm in a child process with a time budget.  A kernel-side protocol bug would otherwise hang
     the whole benchmark (device waits are bounded and trap after 4 s, which poisons the CUDA context): the parent
     kills the exact process group it started and retries once with the conservative kernel paths (per-tap conv
-    boxes, register epilogues).  Under torchrun every rank supervises its own child."""
+    boxes, register epilogues, one execution slot).  Under torchrun every rank supervises its own child."""
     if os.environ.get("TT_BENCH_CHILD") == "1":
         return False
     import signal
 
     budget = 240 + 20 * (args.steps + args.warmup)
-    attempts = [{}, {"TT_CONV_HALO": "0", "TT_GEMM_TS": "0", "TT_GEMM_TE": "0", "TT_BENCH_RETRY": "1"}]
+    attempts = [{}, {"TT_CONV_HALO": "0", "TT_GEMM_TS": "0", "TT_GEMM_TE": "0", "TT_SLOTS": "1", "TT_BENCH_RETRY": "1"}]
     for extra in attempts:
         env = dict(os.environ, TT_BENCH_CHILD="1", **extra)
         p = subprocess.Popen([sys.executable, str(Path(__file__).resolve()), *sys.argv[1:]], env=env, stdout=subprocess.PIPE,
