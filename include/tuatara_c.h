@@ -46,7 +46,8 @@ typedef struct tt_config {
   float low_text;       /* 0.4   tuatara.cpp:399 */
   int min_area;         /* 10    tuatara.cpp:148 */
   int max_batch_pages;  /* pages per group = one PARSeq batch (0 = default 32); CRAFT runs in sub-batches of 8 inside it */
-  int slots_per_gpu;    /* concurrent execution slots (streams + host threads) per GPU: 0 = default 2, max 4 */
+  int slots_per_gpu;    /* concurrent execution slots (streams + host threads) per GPU: 0 = default 1, max 4; 2 overlaps one
+                           group's host phases with another group's kernels (+5 % on large batches, bench.py) */
 } tt_config;
 
 typedef struct tt_item {

@@ -242,14 +242,25 @@ int run_device(tt_engine& e, int g, const tt_image* pages, const std::vector<int
     i = j;
   }
   static const int env_slots = std::getenv("TT_SLOTS") ? std::atoi(std::getenv("TT_SLOTS")) : 0;  // development override
-  const int dflt = env_slots > 0 ? env_slots : 2;
+  const int dflt = env_slots > 0 ? env_slots : 1;  // 2 concurrent slots are opt-in (bench.py): see DESIGN "Known issue"
   const int want = std::min(cfg.slots_per_gpu > 0 ? cfg.slots_per_gpu : dflt, kSlotsPerDevice);
   const int S = std::min<int>(want, static_cast<int>(groups.size()));
   std::vector<int> rcs(S, 0);
   std::vector<std::string> errs(S);
   auto slot_main = [&](int sidx) {
-    DeviceCtx& d = *e.devs[g * kSlotsPerDevice + sidx];
-    std::lock_guard<std::mutex> lock(d.mu);
+    // TT_SLOT_STEAL=1 (development, see DESIGN "Known issue"): take any idle slot instead of queueing on slot sidx
+    static const bool steal = std::getenv("TT_SLOT_STEAL") && std::atoi(std::getenv("TT_SLOT_STEAL")) != 0;
+    DeviceCtx* dp = nullptr;
+    for (int k = 0; steal && k < want && dp == nullptr; ++k) {
+      DeviceCtx& c = *e.devs[g * kSlotsPerDevice + (sidx + k) % want];
+      if (c.mu.try_lock()) dp = &c;
+    }
+    if (dp == nullptr) {
+      dp = e.devs[g * kSlotsPerDevice + sidx].get();
+      dp->mu.lock();
+    }
+    DeviceCtx& d = *dp;
+    std::lock_guard<std::mutex> lock(d.mu, std::adopt_lock);
     if (cudaSetDevice(d.device) != cudaSuccess) { errs[sidx] = "cudaSetDevice failed"; rcs[sidx] = 1; return; }
     for (size_t k = sidx; k < groups.size(); k += S)
       if (run_group(d, cfg, pages, groups[k], opt, results)) { errs[sidx] = last_error(); rcs[sidx] = 1; return; }
