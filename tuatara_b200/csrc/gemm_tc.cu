@@ -976,6 +976,9 @@ bool make_tmap_f32_chunk(CUtensorMap* m, const void* base, long long rows, int c
 bool tma_epilogue_ok(const KParams& kp) {
   static const int te_env = env_int("TT_GEMM_TE", 1);
   const Epilogue& e = kp.epi;
+  // Only for launches that fill the GPU.  Small ones gain nothing from it (latency bound), and two pair-cluster TE
+  // kernels of different streams running side by side on disjoint SMs hung the GPU (DESIGN "Known issue", open).
+  if (te_env != 2 && kp.m_tiles_total < 2 * num_sms()) return false;
   return te_env != 0 && kp.mode == 0 && e.out_type == OUT_F32 && e.res_type == RES_F32 && e.act == ACT_NONE && kp.BN % 32 == 0 &&
          kp.N % 4 == 0 && e.ldc % 4 == 0 && e.ldr % 4 == 0 && (e.res_mod == 0 || e.res_mod % kBlockM == 0) &&
          reinterpret_cast<uintptr_t>(e.out) % 16 == 0 && reinterpret_cast<uintptr_t>(e.residual) % 16 == 0;
