@@ -449,7 +449,7 @@ def supervise(args) -> bool:
         return False
     import signal
 
-    budget = 240 + 20 * (args.steps + args.warmup)
+    budget = env_int("TT_BENCH_BUDGET_S", 240 + 20 * (args.steps + args.warmup))
     attempts = [{}, {"TT_CONV_HALO": "0", "TT_GEMM_TS": "0", "TT_GEMM_TE": "0", "TT_SLOTS": "1", "TT_BENCH_RETRY": "1"}]
     for extra in attempts:
         env = dict(os.environ, TT_BENCH_CHILD="1", **extra)
@@ -489,6 +489,17 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
     elif not supervise(args):
+        fake = os.environ.get("TT_BENCH_TEST_CHILD")  # tests/test_bench_supervisor_cpu.py: exercises kill + retry without a GPU
+        if fake:
+            if fake == "hang_once" and not os.environ.get("TT_BENCH_RETRY"):
+                time.sleep(3600)
+            if fake == "fail_once" and not os.environ.get("TT_BENCH_RETRY"):
+                raise SystemExit(3)
+            if rank == 0:
+                print("NCCL version line that is not JSON")
+                print(json.dumps({"metric": "pages/sec end-to-end", "value": 1.0, "fake": True,
+                                  "retry": bool(os.environ.get("TT_BENCH_RETRY")), "slots": os.environ.get("TT_SLOTS")}), flush=True)
+            return
         run_native(args, rank, local_rank, world)
 
 
