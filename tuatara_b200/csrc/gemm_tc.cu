@@ -994,7 +994,11 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   const int b_rows = kp.pair ? kp.BN / 2 : kp.BN;
   const int a_bytes = kBlockM * row_bytes, b_bytes = b_rows * row_bytes;
   using KernelFn = void (*)(const KParams);
-  const bool te = tma_epilogue_ok(kp);
+  bool te = tma_epilogue_ok(kp);
+  {  // development switch for the open concurrency issue: TT_TE_PAIR=0 keeps the TMA epilogue off CTA-pair launches
+    static const int te_pair_env = env_int("TT_TE_PAIR", 1);
+    if (te && kp.pair && te_pair_env == 0) te = false;
+  }
   static const int ts_env = env_int("TT_GEMM_TS", 1);
   const bool ts = !te && ts_env != 0 && kp.epi.out_type == OUT_BF16 && kp.BN % 32 == 0 && kp.epi.ldc % 8 == 0 &&
                   reinterpret_cast<uintptr_t>(kp.epi.out) % 16 == 0;
