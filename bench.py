@@ -450,7 +450,7 @@ def supervise(args) -> bool:
     import signal
 
     budget = env_int("TT_BENCH_BUDGET_S", 240 + 20 * (args.steps + args.warmup))
-    attempts = [{}, {"TT_CONV_HALO": "0", "TT_GEMM_TS": "0", "TT_GEMM_TE": "0", "TT_SLOTS": "1", "TT_BENCH_RETRY": "1"}]
+    attempts = [{}, {"TT_CONV_HALO": "0", "TT_GEMM_TS": "0", "TT_GEMM_TE": "0", "TT_GEMM_EW": "8", "TT_SLOTS": "1", "TT_BENCH_RETRY": "1"}]
     for extra in attempts:
         env = dict(os.environ, TT_BENCH_CHILD="1", **extra)
         p = subprocess.Popen([sys.executable, str(Path(__file__).resolve()), *sys.argv[1:]], env=env, stdout=subprocess.PIPE,
