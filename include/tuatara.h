@@ -18,6 +18,7 @@
 #define TUATARA_H
 
 #include <cstdint>
+#include <cstdlib>
 #include <iostream>
 #include <map>
 #include <mutex>
@@ -54,13 +55,19 @@ inline tt_engine* engine_for(const std::string& weights_dir) {
   auto it = cache.find(weights_dir);
   if (it != cache.end()) return it->second;
   tt_engine* e = nullptr;
-  if (tt_engine_create(weights_dir.c_str(), nullptr, 0, nullptr, &e) != 0) return nullptr;
+  // devices: the TT_DEVICES environment variable when set ("0,2" / "all"), else every visible GPU -- a batch is cut
+  // into detection units that all of them pull from one queue; a single page simply runs on the first
+  std::vector<int> devs;
+  if (std::getenv("TT_DEVICES") == nullptr)
+    for (int i = 0; i < tt_device_count(); ++i) devs.push_back(i);
+  if (tt_engine_create(weights_dir.c_str(), devs.empty() ? nullptr : devs.data(), static_cast<int>(devs.size()), nullptr, &e) != 0)
+    return nullptr;
   cache[weights_dir] = e;
   return e;
 }
 }  // namespace detail
 
-// Additive batch API: many pages in one call (sharded over the engine's GPUs).
+// Additive batch API: many pages in one call, spread over the engine's GPUs (all visible ones, or TT_DEVICES).
 inline std::vector<std::vector<OutputItem>> image_to_data_batch(const std::vector<ImageView>& images,
                                                                 const std::string& weights_dir,
                                                                 const std::string& outputs_dir) {

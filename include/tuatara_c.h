@@ -45,9 +45,10 @@ typedef struct tt_config {
   float link_threshold; /* 0.4   tuatara.cpp:398 */
   float low_text;       /* 0.4   tuatara.cpp:399 */
   int min_area;         /* 10    tuatara.cpp:148 */
-  int max_batch_pages;  /* pages per group = one PARSeq batch (0 = default 32); CRAFT runs in sub-batches of 8 inside it */
-  int slots_per_gpu;    /* concurrent execution slots (streams + host threads) per GPU: 0 = default 1, max 4; 2 overlaps one
-                           group's host phases with another group's kernels (+5 % on large batches, bench.py) */
+  int max_batch_pages;  /* pages whose crops form one PARSeq batch in a slot (0 = default 32); detection runs in units of <= 8
+                           equally sized pages, crops of pages of any size share the recognition batch */
+  int slots_per_gpu;    /* concurrent execution slots (streams + host threads) per GPU: 0 = default 2, max 4.  Two slots
+                           overlap one batch's host phases with another batch's kernels (+5 %); 1 = strictly serial kernels */
 } tt_config;
 
 typedef struct tt_item {
@@ -68,23 +69,30 @@ TT_API void tt_config_default(tt_config* cfg);
 TT_API const char* tt_last_error(void);
 /* Engine = weights resident on each listed device + streams + workspaces.  Replaces the two
  * torch::jit::load calls per image (tuatara.cpp:333-336, :423-428): weights_dir must hold
- * craft.ttw and parseq.ttw (tuatara_b200.weights exporter).  devices == NULL -> {0}. */
+ * craft.ttw and parseq.ttw (tuatara_b200.weights exporter).  devices == NULL -> the devices named by the TT_DEVICES
+ * environment variable ("0,1,2" or "all"), else {0}. */
 TT_API int tt_engine_create(const char* weights_dir, const int* devices, int n_devices, const tt_config* cfg,
                      tt_engine** out);
 TT_API void tt_engine_destroy(tt_engine* e);
-/* image_to_data (tuatara.cpp:314-512) for a batch of pages; pages are sharded over the engine's
- * GPUs, results gathered on the host in page order. */
+/* CUDA devices visible to this process (0 when there is none: the library has no CPU fallback). */
+TT_API int tt_device_count(void);
+/* image_to_data (tuatara.cpp:314-512) for a batch of pages.  The pages are cut into detection units that the execution
+ * slots of all the engine's GPUs pull from a shared work queue (no collective: pages are independent); results are
+ * gathered on the host in page order. */
 TT_API int tt_ocr_pages(tt_engine* e, const tt_image* pages, int n_pages, tt_result** out);
 /* Same, with options the benchmark and the parity tests need.
  *  pages_on_device: tt_image.data are device pointers (page i on the GPU that gets page i, i.e.
  *    engine device i % n_devices) -- throughput with inputs already resident in HBM.
  *  score_override: NULL, or n_pages pointers (NULL entries allowed) to fp32 [h32/2][w32/2][2] maps
  *    that replace CRAFT's output for that page AFTER CRAFT has run in full (random-init weights
- *    give near-constant maps).  override_on_device: those pointers are device memory. */
+ *    give near-constant maps).  override_on_device: those pointers are device memory.
+ *  Zero-initialise the struct: fields added later default to 0. */
 typedef struct tt_ocr_options {
   int pages_on_device;
   int override_on_device;
   const float* const* score_override;
+  int detect_only;   /* 1: stop after the word boxes (tuatara.cpp:349-418): items carry bbox and an empty text
+                        (BASELINE config "CRAFT detection only") */
 } tt_ocr_options;
 TT_API int tt_ocr_pages_ex(tt_engine* e, const tt_image* pages, int n_pages, const tt_ocr_options* opt, tt_result** out);
 TT_API void tt_result_free(tt_result* r);
@@ -110,6 +118,11 @@ TT_API void tt_profile_dump(const char* path, double* total_ms, double* total_fl
  * parseq_encoder / parseq_decoder :307), flops / bytes being the stage's algorithmic work.  Writes at most
  * cap-1 characters + NUL, returns the full length, clears the log. */
 TT_API int tt_profile_stages(char* buf, int cap);
+
+/* Development aid (TT_TRACE=1 in the environment, off otherwise): where every CTA of the TMEM-allocating kernels stands,
+ * read from a host-mapped progress buffer -- callable from a watchdog thread while a kernel is stuck on the GPU.
+ * Writes at most cap-1 characters + NUL, returns the full length. */
+TT_API int tt_debug_trace_report(char* buf, int cap);
 
 /* ---------------------------------------------------- stage level, host memory */
 /* Size arithmetic of resize_aspect_ratio (tuatara.cpp:211-226), fp32 like the reference. */

@@ -95,7 +95,9 @@ def get_detected_boxes(textmap: torch.Tensor, linkmap: torch.Tensor, text_thresh
             continue
         mask = labels == k  # :150
         max_val = float(textmap_cv[mask].max())  # :151-152 minMaxLoc with mask
-        if max_val < text_threshold:  # :154  (double vs float literal 0.7f promoted)
+        # :154 `if (maxVal < text_threshold)`: double maxVal against the *float* parameter (0.7f, :397) promoted to
+        # double = 0.699999988..., so a component whose maximum is exactly float32(0.7) is KEPT
+        if max_val < float(np.float32(text_threshold)):
             continue
         segmap = np.zeros(textmap_cv.shape, np.uint8)  # :156
         segmap[mask] = 255  # :157

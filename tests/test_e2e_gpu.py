@@ -113,3 +113,43 @@ def test_concurrent_callers_are_serialised_safely(engine):
         for _ in range(3):
             got = list(ex.map(lambda pm: engine.ocr_pages([pm[0]], score_override=[pm[1]])[0], zip(pages, maps)))
             assert got == serial
+
+
+def test_two_slots_small_pages_regression(native_lib):
+    """Round-1 hang (profiles/r2_hang_root_cause.md): two execution slots running SMALL pages concurrently wedged one CTA
+    pair in `tcgen05.alloc.cta_group::2` -- the allocation was issued before the peer CTA had started.  The probe runs
+    the regime that stalled within 0-60 iterations (TMA epilogue forced on small launches, 16-warp GELU epilogue, both
+    slots busy) for 300 iterations per thread; its own watchdog exits with status 3 on a stall."""
+    import os
+    import subprocess
+    import sys as _sys
+
+    from conftest import ROOT
+    env = dict(os.environ, TT_GEMM_TE="2", TT_GEMM_EW="16", PROBE_STALL_S="8", PROBE_TAG="pytest")
+    r = subprocess.run([_sys.executable, str(ROOT / "tools" / "concurrency_probe.py"), "host", "640", "300"], env=env,
+                       capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "concurrent ok [300, 300]" in r.stdout
+
+
+def test_mixed_page_sizes_share_one_recognition_batch(engine):
+    """Pages of different sizes in one request: detection runs per size bucket, the crops of all of them are recognised in
+    one PARSeq batch; every page must equal its single-page result (and the oracle-checked uniform case above)."""
+    shapes = [(640, 768), (1280, 1280), (512, 512), (640, 768), (1000, 754), (512, 512), (1280, 1280), (763, 607)]
+    pages, maps = [], []
+    for i, (h, w) in enumerate(shapes):
+        pages.append(np.ascontiguousarray(synth.synth_page(i)[:h, :w]))
+        _, _, h32, w32, _ = tb.resize_plan(h, w)
+        full = synth.synth_score_maps(i)
+        if max(h, w) > 1024:
+            m = full
+        else:
+            m = np.zeros((h32 // 2, w32 // 2, 2), np.float32)
+            hh, ww = min(h32 // 2, full.shape[0]), min(w32 // 2, full.shape[1])
+            m[:hh, :ww] = full[:hh, :ww]
+        maps.append(np.ascontiguousarray(m))
+    together = engine.ocr_pages(pages, score_override=maps)
+    assert sum(len(p) for p in together) > 500
+    for i in range(len(shapes)):
+        alone = engine.ocr_pages([pages[i]], score_override=[maps[i]])[0]
+        assert alone == together[i], i

@@ -1,5 +1,6 @@
 """Host-side logic of the product (geometry, size arithmetic, tokenizer) through the C ABI, bit-exact
 against cv2 / the oracle / the golden fixtures.  Runs without a GPU."""
+import sys
 from pathlib import Path
 
 import cv2
@@ -125,3 +126,50 @@ def test_decode_matches_reference_tokenizer(native_lib):
     logits[50:100, 2, 88] = 50.0  # class 88 is silently dropped
     ref = [R.truncate_at_eos(t) for t in tok.decode(torch.softmax(logits, -1))]
     assert tb.decode_ids(logits.argmax(-1).numpy().astype(np.int32)) == ref
+
+
+# ---------------------------------------------------------------- pins from the reference's own compiled code
+def _tokenizer_golden():
+    import json
+    return json.loads((GOLD / "tokenizer_ref.json").read_text())
+
+
+def test_tokenizer_pinned_by_reference_binary_golden(native_lib):
+    """tests/golden/tokenizer_ref.json holds the answers of the reference's own `class Tokenizer`
+    (tuatara.cpp:25-117, compiled unmodified by oracle/build_ref.py): table, ids and the strings after the
+    caller-side cut at ']' (:495-502).  Both the oracle restatement and the product's tt_decode must reproduce them."""
+    g = _tokenizer_golden()
+    sys.path.insert(0, str(GOLD))
+    from make_golden_tokenizer import make_logits
+    logits, ids = make_logits(g["seed"], *g["shape"])
+    assert ids.tolist() == g["ids"]
+    want = [bytes.fromhex(h).decode("latin-1") for h in g["strings_hex"]]
+    itos_ref = bytes.fromhex(g["itos_hex"]).decode("latin-1")
+    # oracle restatement
+    tok = R.Tokenizer()
+    assert (tok.itos, tok.eos_id, tok.bos_id, tok.pad_id) == (itos_ref, g["eos_id"], g["bos_id"], g["pad_id"])
+    got_oracle = [R.truncate_at_eos(t) for t in tok.decode(torch.softmax(torch.from_numpy(logits), -1))]
+    assert got_oracle == want
+    # product (host code of the C ABI: tt_tokenizer_table / tt_decode)
+    itos, e, b, p = tb.tokenizer_table()
+    assert (itos, e, b, p) == (itos_ref, g["eos_id"], g["bos_id"], g["pad_id"])
+    assert tb.decode_ids(ids.astype(np.int32)) == want
+    assert sum(1 for w in want if w == "") >= 3 and any("\\" in w for w in want)  # edge cases are in the vectors
+
+
+def test_tokenizer_reference_binary_live(native_lib):
+    """Where the reference tree is present (this container, not the GPU box) the binary is rebuilt and re-run on fresh
+    seeds: reference C++ == oracle == product."""
+    from oracle import build_ref
+    exe = build_ref.build()
+    if exe is None:
+        pytest.skip("/root/reference absent and no prebuilt oracle/_ref/tokenizer_ref")
+    sys.path.insert(0, str(GOLD))
+    from make_golden_tokenizer import make_logits
+    assert build_ref.table() == tb.tokenizer_table()
+    tok = R.Tokenizer()
+    for seed in (1, 2, 3):
+        logits, ids = make_logits(seed, 64)
+        want = build_ref.decode(logits)
+        assert [R.truncate_at_eos(t) for t in tok.decode(torch.softmax(torch.from_numpy(logits), -1))] == want
+        assert tb.decode_ids(ids.astype(np.int32)) == want

@@ -158,9 +158,12 @@ class Engine:
     """Weights resident on the GPU(s) + streams + workspaces (tt_engine_*)."""
 
     def __init__(self, weights_dir: str, devices=None, cfg: _native.tt_config | None = None):
+        """devices: list of CUDA device indices, "all", or None (= the TT_DEVICES environment variable, else device 0)."""
         self._h = C.c_void_p()
         dev = None
         n = 0
+        if isinstance(devices, str) and devices == "all":
+            devices = list(range(lib().tt_device_count()))
         if devices is not None:
             n = len(devices)
             dev = (C.c_int * n)(*devices)
@@ -174,7 +177,7 @@ class Engine:
 
     __del__ = close
 
-    def ocr_pages(self, images: list, score_override: list | None = None) -> list[list[dict]]:
+    def ocr_pages(self, images: list, score_override: list | None = None, detect_only: bool = False) -> list[list[dict]]:
         """images: uint8 [H,W,3] numpy arrays (host) or torch CUDA tensors (already on the device).
         score_override: optional per-page float32 [h32/2, w32/2, 2] maps (numpy or CUDA tensors, or
         None entries) that replace CRAFT's output after CRAFT has run (benchmark / parity tests)."""
@@ -185,7 +188,9 @@ class Engine:
         else:
             structs = [_native.image_struct(im) for im in images]
         arr = (_native.tt_image * n)(*structs)
-        opt = _native.tt_ocr_options(int(on_dev), 0, None)
+        if n and any(isinstance(im, np.ndarray) == on_dev for im in images):
+            raise TuataraError("ocr_pages: host and device pages cannot be mixed in one call")
+        opt = _native.tt_ocr_options(int(on_dev), 0, None, int(detect_only))
         keep = []
         if score_override is not None:
             ov_dev = any(m is not None and not isinstance(m, np.ndarray) for m in score_override)
@@ -237,7 +242,9 @@ _engines: dict = {}
 def _engine_for(weights_dir: str) -> Engine:
     key = str(weights_dir)
     if key not in _engines:
-        _engines[key] = Engine(key)
+        import os
+        # like include/tuatara.h: TT_DEVICES when set, else every visible GPU
+        _engines[key] = Engine(key, devices=None if os.environ.get("TT_DEVICES") else "all")
     return _engines[key]
 
 

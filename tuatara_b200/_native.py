@@ -30,7 +30,7 @@ class tt_config(C.Structure):
 
 class tt_ocr_options(C.Structure):
     _fields_ = [("pages_on_device", C.c_int), ("override_on_device", C.c_int),
-                ("score_override", C.POINTER(C.c_void_p))]
+                ("score_override", C.POINTER(C.c_void_p)), ("detect_only", C.c_int)]
 
 
 class tt_item(C.Structure):
@@ -57,6 +57,7 @@ SIGNATURES = {
     "tt_last_error": (C.c_char_p, []),
     "tt_engine_create": (_I, [C.c_char_p, _PI, _I, C.POINTER(tt_config), C.POINTER(_P)]),
     "tt_engine_destroy": (None, [_P]),
+    "tt_device_count": (_I, []),
     "tt_ocr_pages": (_I, [_P, C.POINTER(tt_image), _I, C.POINTER(C.POINTER(tt_result))]),
     "tt_ocr_pages_ex": (_I, [_P, C.POINTER(tt_image), _I, C.POINTER(tt_ocr_options), C.POINTER(C.POINTER(tt_result))]),
     "tt_result_free": (None, [C.POINTER(tt_result)]),
@@ -68,6 +69,7 @@ SIGNATURES = {
     "tt_profile_collect": (None, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "tt_profile_dump": (None, [C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "tt_profile_stages": (_I, [C.c_char_p, _I]),
+    "tt_debug_trace_report": (_I, [C.c_char_p, _I]),
     "tt_resize_plan": (_I, [_I, _I, _F, _F, _PI, _PI, _PI, _PI, _PF]),
     "tt_preprocess": (_I, [C.POINTER(tt_image), _F, _F, _P]),
     "tt_craft_forward": (_I, [_P, _P, _I, _I, _P]),

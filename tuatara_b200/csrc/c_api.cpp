@@ -2,6 +2,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "postprocess.cuh"
 #include "resize.cuh"
 #include "tokenizer.h"
+#include "trace.h"
 #include "tuatara_c.h"
 
 using namespace tt;
@@ -73,6 +75,15 @@ void tt_config_default(tt_config* cfg) {
 
 const char* tt_last_error(void) { return last_error(); }
 unsigned long long tt_launch_count(void) { return g_launches.load(); }
+
+int tt_debug_trace_report(char* buf, int cap) {
+  const std::string r = trace_report();
+  if (!buf || cap <= 0) return static_cast<int>(r.size());
+  const size_t n = std::min(r.size(), static_cast<size_t>(cap - 1));
+  std::memcpy(buf, r.data(), n);
+  buf[n] = 0;
+  return static_cast<int>(r.size());
+}
 
 int tt_resize_plan(int rows, int cols, float canvas_size, float mag_ratio, int* target_h, int* target_w, int* h32,
                    int* w32, float* ratio) {

@@ -1,5 +1,11 @@
 #include "common.h"
 
+#include <chrono>
+#include <cstdlib>
+#include <thread>
+
+#include "trace.h"
+
 #include <map>
 #include <mutex>
 #include <utility>
@@ -65,6 +71,7 @@ thread_local cudaEvent_t t_stage_open = nullptr;
 
 void stage_begin(cudaStream_t s) {
   if (!prof_enabled()) return;
+  if (t_stage_open != nullptr) { cudaEventDestroy(t_stage_open); t_stage_open = nullptr; }   // left open by an error path
   cudaEvent_t ev;
   if (cudaEventCreate(&ev) != cudaSuccess) return;
   cudaEventRecord(ev, s);
@@ -110,17 +117,44 @@ std::string stage_collect() {
 
 cudaError_t ensure_dynamic_smem(const void* func, int bytes) {
   static std::mutex mu;
-  static std::map<std::pair<const void*, int>, cudaError_t> done;
+  static std::map<std::pair<const void*, int>, int> done;   // largest size set so far per (kernel, device)
   int dev = 0;
   cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(mu);
   auto key = std::make_pair(func, dev);
   auto it = done.find(key);
-  if (it != done.end()) return it->second;
+  if (it != done.end() && it->second >= bytes) return cudaSuccess;
   const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e != cudaSuccess) set_error(std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(e));
-  done[key] = e;
-  return e;
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(e));
+    return e;
+  }
+  done[key] = bytes;
+  return cudaSuccess;
+}
+
+cudaError_t stream_sync(cudaStream_t s) {
+  static const double limit_s = std::getenv("TT_WATCHDOG_S") ? std::atof(std::getenv("TT_WATCHDOG_S")) : 120.0;
+  if (limit_s <= 0) return cudaStreamSynchronize(s);
+  using clock = std::chrono::steady_clock;
+  const auto t0 = clock::now();
+  for (long long spin = 0;; ++spin) {
+    const cudaError_t q = cudaStreamQuery(s);
+    if (q == cudaSuccess) return cudaSuccess;
+    if (q != cudaErrorNotReady) {
+      set_error(std::string("stream failed: ") + cudaGetErrorString(q));
+      return q;
+    }
+    if ((spin & 63) == 63) {
+      const double el = std::chrono::duration<double>(clock::now() - t0).count();
+      if (el > limit_s) {
+        set_error("GPU stall: the stream did not drain within " + std::to_string(static_cast<int>(limit_s)) +
+                  " s (TT_WATCHDOG_S); the device may need a reset\n" + trace_report());
+        return cudaErrorLaunchTimeout;
+      }
+      if (el > 2e-3) std::this_thread::sleep_for(std::chrono::microseconds(20));   // busy-poll the first 2 ms, then back off
+    }
+  }
 }
 
 }  // namespace tt

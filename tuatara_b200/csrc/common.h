@@ -28,8 +28,12 @@ void stage_begin(cudaStream_t s);
 void stage_end(cudaStream_t s, const char* name, double flops, double bytes);
 // "name,count,ms,flops,bytes\n" per stage (summed over the recorded intervals); clears the log.
 std::string stage_collect();
+// cudaStreamSynchronize with a host-side watchdog: polls the stream and gives up after TT_WATCHDOG_S seconds (default
+// 120, 0 = wait forever), so that a stuck kernel becomes an error return (cudaErrorLaunchTimeout + tt_last_error with
+// the device-side trace when TT_TRACE=1) instead of a caller blocked forever.  The stream itself stays stuck.
+cudaError_t stream_sync(cudaStream_t s);
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: set it once per (kernel, device).
-cudaError_t ensure_dynamic_smem(const void* func, int bytes);
+cudaError_t ensure_dynamic_smem(const void* func, int bytes);  // raises the attribute when a later call asks for more
 
 }  // namespace tt
 

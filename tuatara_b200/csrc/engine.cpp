@@ -5,6 +5,9 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <map>
+#include <tuple>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -21,7 +24,7 @@ namespace {
 
 constexpr int kCompCap = 2048;   // compact per-page result block: components
 constexpr int kRowCap = 32768;   //                                row extents
-constexpr int kMaxCropsPerPass = 16384;
+constexpr int kMaxCropsPerPass = 32768;
 constexpr int kCraftSubBatch = 8;   // pages per CRAFT / post-processing pass inside a group
 
 #define E_TRY(expr)                                   \
@@ -68,7 +71,7 @@ int detect_boxes(DeviceCtx& d, const tt_config& cfg, const float* maps_dev, int 
     E_TRY(post_run(ws, maps_dev, pp, d.stream));
     E_CUDA(cudaMemcpyAsync(d.pinned, ws.result, bytes, cudaMemcpyDeviceToHost, d.stream));
     stage_end(d.stream, "postprocess", 0.0, 24.0 * batch * H * W);  // 24 B per map pixel; kernels + the result D2H
-    E_CUDA(cudaStreamSynchronize(d.stream));
+    E_TRY(stream_sync(d.stream));
     g_d2h_bytes += bytes;
     out->assign(batch, {});
     bool ok = true;
@@ -82,75 +85,104 @@ int detect_boxes(DeviceCtx& d, const tt_config& cfg, const float* maps_dev, int 
   return 1;
 }
 
-// One group of equally sized pages on one device.  CRAFT + post-processing run in sub-batches of kCraftSubBatch
-// pages (its activations stay L2-friendlier: bigger batches ran 10 % slower per page), PARSeq runs once over the
-// crops of the whole group (its 27 decoder passes are launch-latency bound: their cost per page falls with the batch).
-int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const std::vector<int>& idx,
-              const tt_ocr_options& opt, std::vector<PageOut>* results) {
+// ---------------------------------------------------------------------------------------------------------------
+// Scheduling.  A request is cut into DETECTION UNITS: up to kCraftSubBatch pages of one size (pages of equal
+// size are bucketed wherever they sit in the request).  Units go into work queues that the execution slots of all GPUs
+// drain with an atomic counter: words per page vary, so static page -> GPU assignment would leave GPUs idle.  A slot
+//   1. runs a unit: upload, resize, CRAFT, post-processing, one small D2H, host geometry, then the crop kernel, which
+//      appends the unit's crops (bf16 patch rows) to the slot's RECOGNITION BATCH -- pages of any size mix there;
+//   2. runs PARSeq over the batch once it holds `max_batch_pages` pages' worth of crops (or the queues are empty):
+//      the decoder's 27 passes are latency bound, their cost per crop falls with the batch.
+// Two slots per GPU by default: one slot's host phases (geometry, result assembly, D2H waits) are covered by the other
+// slot's kernels.
+struct Unit {
+  std::vector<int> pages;   // indices into the request, all of one size
+};
+
+struct CropOwner { int page, box; };
+
+// crops waiting for recognition in one slot (device patch rows live in DeviceCtx::patch_buf)
+struct Pending {
+  std::vector<CropOwner> owner;
+  int pages = 0;
+};
+
+cudaError_t ensure_patch_buf(DeviceCtx& d, size_t crops, size_t keep_crops) {
+  if (crops <= d.patch_cap) return cudaSuccess;
+  size_t cap = std::max<size_t>(crops + crops / 2, 4096);
+  __nv_bfloat16* nb = nullptr;
+  TT_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&nb), cap * 128 * 96 * sizeof(__nv_bfloat16)));
+  if (d.patch_buf && keep_crops)
+    TT_CUDA_TRY(cudaMemcpyAsync(nb, d.patch_buf, keep_crops * 128 * 96 * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, d.stream));
+  if (d.patch_buf) {
+    TT_CUDA_TRY(stream_sync(d.stream));
+    cudaFree(d.patch_buf);
+  }
+  d.patch_buf = nb;
+  d.patch_cap = cap;
+  return cudaSuccess;
+}
+
+// Detection + cropping of one unit (tuatara.cpp:349-418, :437-441).  Fills bbox of every page of the unit, sizes its
+// text vector, appends the crops to the slot's recognition batch.
+int detect_unit(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const Unit& u, const tt_ocr_options& opt,
+                std::vector<PageOut>* results, Pending* pend) {
   const cudaMemcpyKind page_kind = opt.pages_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  const int B = static_cast<int>(idx.size());
-  const int SB = std::min(B, kCraftSubBatch);
-  const tt_image& first = pages[idx[0]];
+  const int nb = static_cast<int>(u.pages.size());
+  const tt_image& first = pages[u.pages[0]];
   int th, tw, h32, w32;
   float ratio;
   resize_plan(first.rows, first.cols, cfg.canvas_size, cfg.mag_ratio, &th, &tw, &h32, &w32, &ratio);
   const size_t page_bytes = static_cast<size_t>(first.rows) * first.cols * 3;
   const size_t in_bytes = static_cast<size_t>(h32) * w32 * 3;
   const size_t page_stride = (page_bytes + 255) & ~size_t(255);
-  const size_t need = d.craft_bytes(SB, h32, w32) + B * (page_stride + 4096) + SB * in_bytes + (8u << 20);
+  const size_t need = d.craft_bytes(nb, h32, w32) + nb * (page_stride + 4096 + in_bytes) + (8u << 20);
+  if (need > d.arena.capacity()) E_TRY(stream_sync(d.stream));   // growing frees the old block: nothing may still use it
   E_TRY(d.arena.reserve(need));
   d.arena.reset();
-  uint8_t* pages_dev = d.arena.get<uint8_t>(B * page_stride);
-  if (!pages_dev) { set_error("arena exhausted (pages)"); return 1; }
-  const size_t mark = d.arena.offset();
-  std::vector<PageRef> refs(B);
-  std::vector<std::vector<DetBox>> det(B);
-  for (int s0 = 0; s0 < B; s0 += SB) {
-    const int nb = std::min(SB, B - s0);
-    d.arena.reset_to(mark);
-    uint8_t* craft_in = d.arena.get<uint8_t>(nb * in_bytes);
-    if (!craft_in) { set_error("arena exhausted (CRAFT input)"); return 1; }
-    stage_begin(d.stream);
-    for (int b = 0; b < nb; ++b) {
-      const tt_image& im = pages[idx[s0 + b]];
-      uint8_t* dst = pages_dev + (s0 + b) * page_stride;
-      if (opt.pages_on_device) {
-        refs[s0 + b] = PageRef{im.data, im.rows, im.cols, im.step};  // already resident: read in place
-      } else {
-        E_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(im.cols) * 3, im.data, im.step,
-                                 static_cast<size_t>(im.cols) * 3, im.rows, page_kind, d.stream));
-        g_h2d_bytes += page_bytes;
-        refs[s0 + b] = PageRef{dst, im.rows, im.cols, static_cast<size_t>(im.cols) * 3};
-      }
-      E_TRY(page_resize_pad(refs[s0 + b].data, im.rows, im.cols, refs[s0 + b].step, craft_in + b * in_bytes, th, tw, h32, w32,
-                            d.stream));
+  uint8_t* pages_dev = d.arena.get<uint8_t>(nb * page_stride);
+  uint8_t* craft_in = d.arena.get<uint8_t>(nb * in_bytes);
+  if (!pages_dev || !craft_in) { set_error("arena exhausted (pages)"); return 1; }
+  std::vector<PageRef> refs(nb);
+  stage_begin(d.stream);
+  for (int b = 0; b < nb; ++b) {
+    const tt_image& im = pages[u.pages[b]];
+    uint8_t* dst = pages_dev + b * page_stride;
+    if (opt.pages_on_device) {
+      refs[b] = PageRef{im.data, im.rows, im.cols, im.step};  // already resident: read in place
+    } else {
+      E_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(im.cols) * 3, im.data, im.step, static_cast<size_t>(im.cols) * 3, im.rows,
+                               page_kind, d.stream));
+      g_h2d_bytes += page_bytes;
+      refs[b] = PageRef{dst, im.rows, im.cols, static_cast<size_t>(im.cols) * 3};
     }
-    stage_end(d.stream, "preprocess", 0.0, static_cast<double>(nb) * (page_bytes + in_bytes));
-    float* maps = nullptr;
-    stage_begin(d.stream);
-    E_TRY(d.craft_forward(craft_in, nb, h32, w32, &maps));
-    // 27 convolutions of CRAFT: 711.4 FLOP per input pixel (= 746.0 GFLOP at 1024 x 1024)
-    stage_end(d.stream, "craft", 746.0e9 / (1024.0 * 1024.0) * nb * h32 * w32, 0.0);
-    if (opt.score_override) {
-      const size_t map_elems = static_cast<size_t>(h32 / 2) * (w32 / 2) * 2;
-      for (int b = 0; b < nb; ++b)
-        if (opt.score_override[idx[s0 + b]]) {
-          E_CUDA(cudaMemcpyAsync(maps + b * map_elems, opt.score_override[idx[s0 + b]], map_elems * sizeof(float),
-                                 opt.override_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d.stream));
-          if (!opt.override_on_device) g_h2d_bytes += map_elems * sizeof(float);
-        }
-    }
-    std::vector<std::vector<DetBox>> sub;
-    if (detect_boxes(d, cfg, maps, nb, h32 / 2, w32 / 2, &sub)) return 1;
-    for (int b = 0; b < nb; ++b) det[s0 + b] = std::move(sub[b]);
+    E_TRY(page_resize_pad(refs[b].data, im.rows, im.cols, refs[b].step, craft_in + b * in_bytes, th, tw, h32, w32, d.stream));
   }
+  stage_end(d.stream, "preprocess", 0.0, static_cast<double>(nb) * (page_bytes + in_bytes));
+  float* maps = nullptr;
+  stage_begin(d.stream);
+  E_TRY(d.craft_forward(craft_in, nb, h32, w32, &maps));
+  // 27 convolutions of CRAFT: 711.4 FLOP per input pixel (= 746.0 GFLOP at 1024 x 1024)
+  stage_end(d.stream, "craft", 746.0e9 / (1024.0 * 1024.0) * nb * h32 * w32, 0.0);
+  if (opt.score_override) {
+    const size_t map_elems = static_cast<size_t>(h32 / 2) * (w32 / 2) * 2;
+    for (int b = 0; b < nb; ++b)
+      if (opt.score_override[u.pages[b]]) {
+        E_CUDA(cudaMemcpyAsync(maps + b * map_elems, opt.score_override[u.pages[b]], map_elems * sizeof(float),
+                               opt.override_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, d.stream));
+        if (!opt.override_on_device) g_h2d_bytes += map_elems * sizeof(float);
+      }
+  }
+  std::vector<std::vector<DetBox>> det;
+  if (detect_boxes(d, cfg, maps, nb, h32 / 2, w32 / 2, &det)) return 1;
 
   // host: rescale boxes, bounding rects, output bboxes (tuatara.cpp:406-418, :256-274)
   const float inv = 1.f / ratio;  // ratio_w == ratio_h (tuatara.cpp:360-361)
   std::vector<CropBox> crops;
-  for (int b = 0; b < B; ++b) {
-    PageOut& po = (*results)[idx[b]];
-    const tt_image& im = pages[idx[b]];
+  for (int b = 0; b < nb; ++b) {
+    PageOut& po = (*results)[u.pages[b]];
+    const tt_image& im = pages[u.pages[b]];
+    int k = 0;
     for (const DetBox& db : det[b]) {
       const RotatedRect adj = adjust_rect(db.rect, inv, inv, 2.f);
       std::array<float, 4> bb;
@@ -160,118 +192,103 @@ int run_group(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const s
       const int x0 = std::max(r.x, 0), y0 = std::max(r.y, 0);
       const int x1 = std::min(r.x + r.w, im.cols), y1 = std::min(r.y + r.h, im.rows);
       crops.push_back(CropBox{b, x0, y0, std::max(x1 - x0, 0), std::max(y1 - y0, 0)});
+      pend->owner.push_back(CropOwner{u.pages[b], k++});
     }
+    po.text.resize(po.bbox.size());   // zero boxes: the reference crashes in torch::cat({}) (tuatara.cpp:485); we return no items
   }
   const int n = static_cast<int>(crops.size());
-  if (n == 0) return 0;  // the reference crashes in torch::cat({}) (tuatara.cpp:485); we return no items
-
-  // crops -> PARSeq, in passes of bounded size; the page buffers stay where they are in the arena,
-  // everything CRAFT allocated after them is recycled
-  std::vector<int> all_ids(static_cast<size_t>(n) * d.w->pd.L);
-  for (int c0 = 0; c0 < n; c0 += kMaxCropsPerPass) {
-    const int nc = std::min(kMaxCropsPerPass, n - c0);
-    // recycle: keep the page buffers by re-reserving on top of them
-    const size_t keep = B * page_stride + 8192;
-    const size_t need2 = keep + d.parseq_bytes(nc) + static_cast<size_t>(nc) * (128 * 96 * 2 + sizeof(CropBox)) +
-                         B * sizeof(PageRef) + (4u << 20);
-    if (need2 > d.arena.capacity()) {
-      // growing would move the page buffers: re-upload is simpler than copying device to device
-      E_TRY(d.arena.reserve(need2));
-      d.arena.reset();
-      pages_dev = d.arena.get<uint8_t>(B * page_stride);
-      for (int b = 0; b < B; ++b) {
-        const tt_image& im = pages[idx[b]];
-        uint8_t* dst = pages_dev + b * page_stride;
-        if (opt.pages_on_device) continue;
-        E_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(im.cols) * 3, im.data, im.step,
-                                 static_cast<size_t>(im.cols) * 3, im.rows, page_kind, d.stream));
-        refs[b].data = dst;
-      }
-    } else {
-      d.arena.reset_to(mark);
-    }
-    PageRef* refs_dev = d.arena.get<PageRef>(B);
-    CropBox* boxes_dev = d.arena.get<CropBox>(nc);
-    __nv_bfloat16* patches = d.arena.get<__nv_bfloat16>(static_cast<size_t>(nc) * 128 * 96);
-    if (!refs_dev || !boxes_dev || !patches) { set_error("arena exhausted (crops)"); return 1; }
-    E_CUDA(cudaMemcpyAsync(refs_dev, refs.data(), sizeof(PageRef) * B, cudaMemcpyHostToDevice, d.stream));
-    E_CUDA(cudaMemcpyAsync(boxes_dev, crops.data() + c0, sizeof(CropBox) * nc, cudaMemcpyHostToDevice, d.stream));
-    g_h2d_bytes += sizeof(PageRef) * B + sizeof(CropBox) * nc + sizeof(int) * nc * d.w->pd.L /*token init*/;
-    g_d2h_bytes += sizeof(int) * nc * d.w->pd.L;
-    stage_begin(d.stream);
-    E_TRY(crop_resize(refs_dev, boxes_dev, nc, nullptr, patches, d.stream));
-    {
-      double src = 0;
-      for (int c = c0; c < c0 + nc; ++c) src += 3.0 * crops[c].w * crops[c].h;
-      stage_end(d.stream, "crop_resize", 0.0, src + static_cast<double>(nc) * 128 * 96 * 2);  // source rect + bf16 patch rows
-    }
-    float* logits = nullptr;
-    int* ids = nullptr;
-    E_TRY(d.parseq_forward(patches, nc, nullptr, &logits, &ids));
-    E_CUDA(cudaMemcpyAsync(all_ids.data() + static_cast<size_t>(c0) * d.w->pd.L, ids, sizeof(int) * nc * d.w->pd.L,
-                           cudaMemcpyDeviceToHost, d.stream));
-    E_CUDA(cudaStreamSynchronize(d.stream));
+  if (opt.detect_only) {   // boxes only: nothing joins the recognition batch
+    pend->owner.resize(pend->owner.size() - n);
+    return 0;
   }
-  // tokenizer (tuatara.cpp:492-505)
-  int c = 0;
-  for (int b = 0; b < B; ++b) {
-    PageOut& po = (*results)[idx[b]];
-    for (size_t k = 0; k < det[b].size(); ++k, ++c)
-      po.text.push_back(decode_ids(all_ids.data() + static_cast<size_t>(c) * d.w->pd.L, d.w->pd.L));
-  }
+  pend->pages += nb;
+  if (n == 0) return 0;
+  const size_t have = pend->owner.size() - n;
+  E_TRY(ensure_patch_buf(d, have + n, have));
+  PageRef* refs_dev = d.arena.get<PageRef>(nb);
+  CropBox* boxes_dev = d.arena.get<CropBox>(n);
+  if (!refs_dev || !boxes_dev) { set_error("arena exhausted (crops)"); return 1; }
+  E_CUDA(cudaMemcpyAsync(refs_dev, refs.data(), sizeof(PageRef) * nb, cudaMemcpyHostToDevice, d.stream));
+  E_CUDA(cudaMemcpyAsync(boxes_dev, crops.data(), sizeof(CropBox) * n, cudaMemcpyHostToDevice, d.stream));
+  g_h2d_bytes += sizeof(PageRef) * nb + sizeof(CropBox) * n;
+  stage_begin(d.stream);
+  E_TRY(crop_resize(refs_dev, boxes_dev, n, nullptr, d.patch_buf + have * 128 * 96, d.stream));
+  double src = 0;
+  for (const CropBox& c : crops) src += 3.0 * c.w * c.h;
+  stage_end(d.stream, "crop_resize", 0.0, src + static_cast<double>(n) * 128 * 96 * 2);  // source rect + bf16 patch rows
   return 0;
 }
 
-// All pages assigned to one GPU: consecutive pages of identical size form groups of <= max_batch pages;
-// group k runs on slot k % kSlotsPerDevice, the slots run concurrently from their own host threads.
-int run_device(tt_engine& e, int g, const tt_image* pages, const std::vector<int>& mine, const tt_ocr_options& opt,
-               std::vector<PageOut>* results, std::string* err) {
+// PARSeq + tokenizer over the slot's recognition batch (tuatara.cpp:450-505).
+int recognise(DeviceCtx& d, std::vector<PageOut>* results, Pending* pend) {
+  const int n = static_cast<int>(pend->owner.size());
+  const int L = d.w->pd.L;
+  for (int c0 = 0; c0 < n; c0 += kMaxCropsPerPass) {
+    const int nc = std::min(kMaxCropsPerPass, n - c0);
+    const size_t need = d.parseq_bytes(nc) + (4u << 20);
+    if (need > d.arena.capacity()) E_TRY(stream_sync(d.stream));
+    E_TRY(d.arena.reserve(need));
+    d.arena.reset();
+    float* logits = nullptr;
+    int* ids = nullptr;
+    E_TRY(d.parseq_forward(d.patch_buf + static_cast<size_t>(c0) * 128 * 96, nc, nullptr, &logits, &ids));
+    const size_t bytes = sizeof(int) * static_cast<size_t>(nc) * L;
+    E_TRY(d.ensure_pinned(bytes));
+    E_CUDA(cudaMemcpyAsync(d.pinned, ids, bytes, cudaMemcpyDeviceToHost, d.stream));
+    g_d2h_bytes += bytes;
+    E_TRY(stream_sync(d.stream));
+    const int* host_ids = reinterpret_cast<const int*>(d.pinned);
+    for (int c = 0; c < nc; ++c) {   // tokenizer (tuatara.cpp:492-505)
+      const CropOwner& o = pend->owner[c0 + c];
+      (*results)[o.page].text[o.box] = decode_ids(host_ids + static_cast<size_t>(c) * L, L);
+    }
+  }
+  pend->owner.clear();
+  pend->pages = 0;
+  return 0;
+}
+
+struct WorkQueues {
+  std::vector<Unit> units;
+  std::vector<std::vector<int>> per_dev;   // unit indices bound to a device (pages resident there)
+  std::vector<int> shared;                 // unit indices any device may take (host pages)
+  std::vector<std::atomic<int>> next_dev;
+  std::atomic<int> next_shared{0};
+  explicit WorkQueues(int G) : per_dev(G), next_dev(G) { for (auto& a : next_dev) a.store(0); }
+  // next unit for a slot of device g, or -1
+  int pop(int g) {
+    const int i = next_dev[g].fetch_add(1);
+    if (i < static_cast<int>(per_dev[g].size())) return per_dev[g][i];
+    const int j = next_shared.fetch_add(1);
+    if (j < static_cast<int>(shared.size())) return shared[j];
+    return -1;
+  }
+};
+
+// One execution slot draining the queues.
+void slot_worker(tt_engine& e, int g, int sidx, int want, const tt_image* pages, const tt_ocr_options& opt, WorkQueues* q,
+                 std::vector<PageOut>* results, int* rc, std::string* err) {
+  // take an idle slot of this GPU if there is one (concurrent callers spread over the slots), else queue on our own
+  DeviceCtx* dp = nullptr;
+  for (int k = 0; k < want && dp == nullptr; ++k) {
+    DeviceCtx& c = *e.devs[g * kSlotsPerDevice + (sidx + k) % want];
+    if (c.mu.try_lock()) dp = &c;
+  }
+  if (dp == nullptr) {
+    dp = e.devs[g * kSlotsPerDevice + sidx].get();
+    dp->mu.lock();
+  }
+  DeviceCtx& d = *dp;
+  std::lock_guard<std::mutex> lock(d.mu, std::adopt_lock);
+  if (cudaSetDevice(d.device) != cudaSuccess) { *err = "cudaSetDevice failed"; *rc = 1; return; }
   const tt_config& cfg = e.cfg;
   const int max_b = cfg.max_batch_pages > 0 ? cfg.max_batch_pages : 32;
-  std::vector<std::vector<int>> groups;
-  size_t i = 0;
-  while (i < mine.size()) {
-    std::vector<int> grp{mine[i]};
-    size_t j = i + 1;
-    while (j < mine.size() && static_cast<int>(grp.size()) < max_b && pages[mine[j]].rows == pages[mine[i]].rows &&
-           pages[mine[j]].cols == pages[mine[i]].cols) {
-      grp.push_back(mine[j]);
-      ++j;
-    }
-    groups.push_back(std::move(grp));
-    i = j;
+  Pending pend;
+  for (int ui = q->pop(g); ui >= 0; ui = q->pop(g)) {
+    if (detect_unit(d, cfg, pages, q->units[ui], opt, results, &pend)) { *err = last_error(); *rc = 1; return; }
+    if (pend.pages >= max_b && recognise(d, results, &pend)) { *err = last_error(); *rc = 1; return; }
   }
-  static const int env_slots = std::getenv("TT_SLOTS") ? std::atoi(std::getenv("TT_SLOTS")) : 0;  // development override
-  const int dflt = env_slots > 0 ? env_slots : 1;  // 2 concurrent slots are opt-in (bench.py): see DESIGN "Known issue"
-  const int want = std::min(cfg.slots_per_gpu > 0 ? cfg.slots_per_gpu : dflt, kSlotsPerDevice);
-  const int S = std::min<int>(want, static_cast<int>(groups.size()));
-  std::vector<int> rcs(S, 0);
-  std::vector<std::string> errs(S);
-  auto slot_main = [&](int sidx) {
-    // TT_SLOT_STEAL=1 (development, see DESIGN "Known issue"): take any idle slot instead of queueing on slot sidx
-    static const bool steal = std::getenv("TT_SLOT_STEAL") && std::atoi(std::getenv("TT_SLOT_STEAL")) != 0;
-    DeviceCtx* dp = nullptr;
-    for (int k = 0; steal && k < want && dp == nullptr; ++k) {
-      DeviceCtx& c = *e.devs[g * kSlotsPerDevice + (sidx + k) % want];
-      if (c.mu.try_lock()) dp = &c;
-    }
-    if (dp == nullptr) {
-      dp = e.devs[g * kSlotsPerDevice + sidx].get();
-      dp->mu.lock();
-    }
-    DeviceCtx& d = *dp;
-    std::lock_guard<std::mutex> lock(d.mu, std::adopt_lock);
-    if (cudaSetDevice(d.device) != cudaSuccess) { errs[sidx] = "cudaSetDevice failed"; rcs[sidx] = 1; return; }
-    for (size_t k = sidx; k < groups.size(); k += S)
-      if (run_group(d, cfg, pages, groups[k], opt, results)) { errs[sidx] = last_error(); rcs[sidx] = 1; return; }
-  };
-  std::vector<std::thread> th;
-  for (int sidx = 1; sidx < S; ++sidx) th.emplace_back(slot_main, sidx);
-  if (S > 0) slot_main(0);
-  for (auto& t : th) t.join();
-  for (int sidx = 0; sidx < S; ++sidx)
-    if (rcs[sidx]) { *err = errs[sidx]; return 1; }
-  return 0;
+  if (recognise(d, results, &pend)) { *err = last_error(); *rc = 1; return; }
 }
 
 }  // namespace
@@ -289,9 +306,24 @@ int tt_engine_create(const char* weights_dir, const int* devices, int n_devices,
     }
     std::unique_ptr<tt_engine> e(new tt_engine);
     if (cfg) e->cfg = *cfg; else tt_config_default(&e->cfg);
+    e->slots.store(e->cfg.slots_per_gpu);
     std::vector<int> devs;
-    if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
-    else devs.push_back(0);
+    if (devices && n_devices > 0) {
+      devs.assign(devices, devices + n_devices);
+    } else if (const char* ev = std::getenv("TT_DEVICES")) {   // "all" or a comma-separated list
+      if (std::strcmp(ev, "all") == 0) {
+        for (int i = 0; i < count; ++i) devs.push_back(i);
+      } else {
+        for (const char* p = ev; *p;) {
+          char* end = nullptr;
+          const long v = std::strtol(p, &end, 10);
+          if (end == p) { set_error(std::string("TT_DEVICES: cannot parse '") + ev + "'"); return 1; }
+          devs.push_back(static_cast<int>(v));
+          p = (*end == ',') ? end + 1 : end;
+        }
+      }
+    }
+    if (devs.empty()) devs.push_back(0);
     for (int dv : devs) {
       if (dv < 0 || dv >= count) { set_error("invalid device index " + std::to_string(dv)); return 1; }
       std::shared_ptr<DeviceWeights> shared;
@@ -314,8 +346,14 @@ int tt_engine_create(const char* weights_dir, const int* devices, int n_devices,
 
 void tt_engine_destroy(tt_engine* e) { delete e; }
 
+int tt_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return count;
+}
+
 void tt_engine_set_slots(tt_engine* e, int slots) {
-  if (e) e->cfg.slots_per_gpu = slots;
+  if (e) e->slots.store(slots);
 }
 
 void* tt_engine_stream(tt_engine* e, int idx) {
@@ -348,28 +386,59 @@ int tt_ocr_pages(tt_engine* e, const tt_image* pages, int n_pages, tt_result** o
 
 int tt_ocr_pages_ex(tt_engine* e, const tt_image* pages, int n_pages, const tt_ocr_options* opt_in, tt_result** out) {
   try {
-    tt_ocr_options opt{0, 0, nullptr};
+    tt_ocr_options opt{0, 0, nullptr, 0};
     if (opt_in) opt = *opt_in;
     if (!e || !out) { set_error("tt_ocr_pages: null argument"); return 1; }
-    for (int i = 0; i < n_pages; ++i)
+    if (n_pages < 0 || (n_pages > 0 && !pages)) { set_error("tt_ocr_pages: bad page array"); return 1; }
+    for (int i = 0; i < n_pages; ++i) {
       if (!pages[i].data || pages[i].rows <= 0 || pages[i].cols <= 0 || pages[i].channels != 3) {
         set_error("Error reading image from file");  // tuatara.cpp:344-347
         return 1;
       }
+      if (pages[i].step < static_cast<size_t>(pages[i].cols) * 3) { set_error("tt_ocr_pages: row step smaller than cols * 3"); return 1; }
+    }
     std::vector<PageOut> results(n_pages);
     const int G = e->n_devices;
-    std::vector<std::vector<int>> shard(G);
-    for (int i = 0; i < n_pages; ++i) shard[i % G].push_back(i);  // page i -> GPU i mod G
-    std::vector<std::string> errs(G);
-    std::vector<int> rcs(G, 0);
-    std::vector<std::thread> workers;
-    for (int g = 0; g < G; ++g) {
-      if (shard[g].empty()) continue;
-      workers.emplace_back([&, g] { rcs[g] = run_device(*e, g, pages, shard[g], opt, &results, &errs[g]); });
+    // detection units: pages of equal size, wherever they sit in the request; device-resident pages stay on their GPU
+    WorkQueues q(G);
+    {
+      std::map<std::tuple<int, int, int>, int> open;   // (device or -1, rows, cols) -> unit being filled
+      for (int i = 0; i < n_pages; ++i) {
+        const int dev = opt.pages_on_device ? i % G : -1;
+        const auto key = std::make_tuple(dev, pages[i].rows, pages[i].cols);
+        auto it = open.find(key);
+        if (it == open.end() || static_cast<int>(q.units[it->second].pages.size()) >= kCraftSubBatch) {
+          q.units.emplace_back();
+          const int ui = static_cast<int>(q.units.size()) - 1;
+          open[key] = ui;
+          if (dev >= 0) q.per_dev[dev].push_back(ui); else q.shared.push_back(ui);
+          it = open.find(key);
+        }
+        q.units[it->second].pages.push_back(i);
+      }
     }
+    static const int env_slots = std::getenv("TT_SLOTS") ? std::atoi(std::getenv("TT_SLOTS")) : 0;  // development override
+    const int cfg_slots = e->slots.load();
+    const int want = std::max(1, std::min(cfg_slots > 0 ? cfg_slots : env_slots > 0 ? env_slots : 2, kSlotsPerDevice));
+    // workers: device-major round robin, so that a short request touches every GPU before any second slot
+    struct W { int g, sidx; };
+    std::vector<W> ws;
+    size_t shared_claimed = 0;
+    for (int sidx = 0; sidx < want; ++sidx)
+      for (int g = 0; g < G; ++g) {
+        if (static_cast<size_t>(sidx) < q.per_dev[g].size()) ws.push_back(W{g, sidx});
+        else if (shared_claimed < q.shared.size()) { ++shared_claimed; ws.push_back(W{g, sidx}); }
+      }
+    if (ws.empty() && n_pages > 0) ws.push_back(W{0, 0});
+    std::vector<std::string> errs(ws.size());
+    std::vector<int> rcs(ws.size(), 0);
+    std::vector<std::thread> workers;
+    for (size_t w = 1; w < ws.size(); ++w)
+      workers.emplace_back([&, w] { slot_worker(*e, ws[w].g, ws[w].sidx, want, pages, opt, &q, &results, &rcs[w], &errs[w]); });
+    if (!ws.empty()) slot_worker(*e, ws[0].g, ws[0].sidx, want, pages, opt, &q, &results, &rcs[0], &errs[0]);
     for (auto& w : workers) w.join();
-    for (int g = 0; g < G; ++g)
-      if (rcs[g]) { set_error("device " + std::to_string(e->devs[g * kSlotsPerDevice]->device) + ": " + errs[g]); return 1; }
+    for (size_t w = 0; w < ws.size(); ++w)
+      if (rcs[w]) { set_error("device " + std::to_string(e->devs[ws[w].g * kSlotsPerDevice]->device) + ": " + errs[w]); return 1; }
     // host-side gather into the C result
     tt_result* r = new tt_result;
     r->n_pages = n_pages;
@@ -417,7 +486,7 @@ int tt_craft_forward(tt_engine* e, const uint8_t* craft_input, int h32, int w32,
     float* maps = nullptr;
     E_TRY(d.craft_forward(in, 1, h32, w32, &maps));
     E_CUDA(cudaMemcpyAsync(maps_out, maps, sizeof(float) * (h32 / 2) * (w32 / 2) * 2, cudaMemcpyDeviceToHost, d.stream));
-    E_CUDA(cudaStreamSynchronize(d.stream));
+    E_TRY(stream_sync(d.stream));
     return 0;
   } catch (const std::exception& ex) {
     set_error(std::string("tt_craft_forward: ") + ex.what());
@@ -456,7 +525,7 @@ int tt_parseq_forward(tt_engine* e, const uint8_t* crops, int n, const int32_t* 
                                  cudaMemcpyDeviceToHost, d.stream));
       if (ids_out)
         E_CUDA(cudaMemcpyAsync(ids_out + static_cast<size_t>(c0) * L, ids, sizeof(int) * nc * L, cudaMemcpyDeviceToHost, d.stream));
-      E_CUDA(cudaStreamSynchronize(d.stream));
+      E_TRY(stream_sync(d.stream));
     }
     return 0;
   } catch (const std::exception& ex) {

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -70,10 +71,10 @@ struct DeviceWeights {
   ~DeviceWeights();
 };
 
-// One execution slot: a stream with its own scratch arena and workspaces.  Each GPU runs kSlotsPerDevice
+// One execution slot: a stream with its own scratch arena and workspaces.  Each GPU runs up to kSlotsPerDevice
 // of them from separate host threads so that one slot's host-side phases (box geometry, result
 // assembly, D2H waits) are covered by the other slot's kernels.
-constexpr int kSlotsPerDevice = 4;   // upper bound; tt_config.slots_per_gpu picks how many run (default 2)
+constexpr int kSlotsPerDevice = 4;   // upper bound; tt_config.slots_per_gpu picks how many run (0 = default 2)
 
 struct DeviceCtx {
   int device = 0;
@@ -81,6 +82,8 @@ struct DeviceCtx {
   std::shared_ptr<DeviceWeights> w;
   Arena arena;
   PostWorkspace post;           // sized lazily for (batch, H, W)
+  __nv_bfloat16* patch_buf = nullptr;  // recognition batch: bf16 patch rows [crops * 128][96] of the crops awaiting PARSeq
+  size_t patch_cap = 0;                //   capacity in crops
   uint8_t* pinned = nullptr;    // host staging for D2H of post results / ids
   size_t pinned_bytes = 0;
   std::mutex mu;                // one request at a time per device
@@ -102,6 +105,7 @@ struct DeviceCtx {
 
 struct tt_engine {
   tt_config cfg;
+  std::atomic<int> slots{0};   // live value of cfg.slots_per_gpu (tt_engine_set_slots may change it between calls)
   int n_devices = 0;
   std::vector<std::unique_ptr<tt::DeviceCtx>> devs;  // [device g][slot s] at g * kSlotsPerDevice + s
 };

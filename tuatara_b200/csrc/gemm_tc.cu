@@ -30,6 +30,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "trace.h"
 
 namespace tt {
 
@@ -71,6 +72,9 @@ struct KParams {
   int b_resident;  // 1: the CTA's [BN x K] weight slice is loaded once and stays in smem; only A streams
   int debug;       // TT_GEMM_DEBUG (development only): 1 = skip epilogue stores, 2 = skip TMEM loads + math + stores
   unsigned long long* dbg_out;  // TT_GEMM_DEBUG & 4: per-role wait/busy cycle counters of CTA 0
+  uint32_t* trace;              // TT_TRACE=1 (trace.h): host-mapped progress buffer, nullptr otherwise
+  uint32_t serial;              //   launch serial inside it
+  int alloc_sync;               // PAIR: cluster barrier before the TMEM allocation (1; 0 = the round-1 order, regression probe only)
   Epilogue epi;
 };
 
@@ -216,6 +220,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
   const bool dbgt = (p.debug & 4) != 0;
 
   if (threadIdx.x == 0) {
+    trace_mark(p.trace, p.serial, blockIdx.x, TR_ENTER);
     ptx::prefetch_tmap(&p.tmA[0]);
     ptx::prefetch_tmap(&p.tmB);
     if (p.kb_src[1] > 0) ptx::prefetch_tmap(&p.tmA[1]);
@@ -239,17 +244,30 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
     }
     ptx::fence_barrier_init();
   }
+  // PAIR: tcgen05.alloc.cta_group::2 is a collective of the two CTAs.  Issued while the peer CTA has not started on its
+  // SM yet, the peer's own alloc never returns (no trap, the cluster hangs in its first barrier).  A cluster's CTAs
+  // are co-scheduled but do not start in the same cycle, and next to kernels of another stream the skew gets large
+  // enough to hit this: root cause of the round-1 "two slots" hang (profiles/r2_hang_root_cause.md).
+  // So: cluster barrier FIRST (it also publishes the peer's mbarrier initialisation), then the allocation.
+  // TT_PAIR_ALLOC_SYNC=0 restores the old order (alloc, then the barrier) for the regression probe.
+  if constexpr (PAIR) {
+    if (p.alloc_sync) ptx::cluster_sync_all();
+  }
   if (warp == 1) {
     if constexpr (PAIR) ptx::tmem_alloc_pair(&ctl->tmem_base, kTmemCols);
     else ptx::tmem_alloc(&ctl->tmem_base, kTmemCols);
+    if (lane == 0) { trace_role_done(p.trace, p.serial, blockIdx.x, kTraceAllocByte); trace_tmem_event(p.trace, p.serial, blockIdx.x, 1); }
   }
   if constexpr (OUT == OUT_CLS_TAIL) {
     for (int i = threadIdx.x; i < 16 * 16 + 16 + 2 * 16 + 2; i += kThreads) ctl->tail[i] = p.epi.tail[i];
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if constexpr (PAIR) ptx::cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  if constexpr (PAIR) {
+    if (!p.alloc_sync) ptx::cluster_sync_all();
+  }
   ptx::tc_fence_after();
+  if (threadIdx.x == 0) trace_mark(p.trace, p.serial, blockIdx.x, TR_SYNC0);
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
 
   if (warp == 0) {
@@ -771,13 +789,17 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
     }
   }
 
+  if (lane == 0) trace_role_done(p.trace, p.serial, blockIdx.x, warp);
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_mark(p.trace, p.serial, blockIdx.x, TR_SYNC1);
   if constexpr (PAIR) ptx::cluster_sync_all();  // neither CTA exits (or frees TMEM) while its peer still works
+  if (threadIdx.x == 0) trace_mark(p.trace, p.serial, blockIdx.x, TR_CSYNC1);
   if (warp == 1) {
     ptx::tc_fence_after();
     if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
     else ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (lane == 0) { trace_role_done(p.trace, p.serial, blockIdx.x, kTraceFreeByte); trace_tmem_event(p.trace, p.serial, blockIdx.x, 2); }
   }
 }
 
@@ -925,9 +947,8 @@ int epi_warps(const Epilogue& e, int BN) {
   if (e.out_type == OUT_CLS_TAIL) return 8;
   if (ew_env == 8) return 8;
   if (ew_env == 16) return (e.out_type == OUT_BF16 && e.act == ACT_GELU && BN % 128 == 0) ? 16 : 8;
-  // 16 warps for the GELU tiles is +1 % end to end, but the 576-thread kernel is one of the two ingredients of the
-  // open concurrency hang (pair TMA-epilogue kernels next to it on other SMs; DESIGN "Known issue"): off by default.
-  return 8;
+  // 16 warps for the MUFU-bound GELU tiles: +1 % end to end (profiles/r1c_ab_switches.md)
+  return (e.out_type == OUT_BF16 && e.act == ACT_GELU && BN % 128 == 0) ? 16 : 8;
 }
 
 template <bool PAIR>
@@ -979,8 +1000,8 @@ bool make_tmap_f32_chunk(CUtensorMap* m, const void* base, long long rows, int c
 bool tma_epilogue_ok(const KParams& kp) {
   static const int te_env = env_int("TT_GEMM_TE", 1);
   const Epilogue& e = kp.epi;
-  // Only for launches that fill the GPU.  Small ones gain nothing from it (latency bound), and two pair-cluster TE
-  // kernels of different streams running side by side on disjoint SMs hung the GPU (DESIGN "Known issue", open).
+  // Only for launches that fill the GPU: small ones are latency bound and gain nothing from the extra two warps and the
+  // 64 KB ring (TT_GEMM_TE=2 forces it everywhere: the regime of the round-1 hang, kept for the regression probe).
   if (te_env != 2 && kp.m_tiles_total < 2 * num_sms()) return false;
   return te_env != 0 && kp.mode == 0 && e.out_type == OUT_F32 && e.res_type == RES_F32 && e.act == ACT_NONE && kp.BN % 32 == 0 &&
          kp.N % 4 == 0 && e.ldc % 4 == 0 && e.ldr % 4 == 0 && (e.res_mod == 0 || e.res_mod % kBlockM == 0) &&
@@ -1055,6 +1076,14 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   kp.dbg_out = dbg_buf;
   if (dbg & 4) cudaMemset(dbg_buf, 0, 16 * sizeof(unsigned long long));
   char tag[128];
+  static const int alloc_sync_env = env_int("TT_PAIR_ALLOC_SYNC", 1);
+  kp.alloc_sync = alloc_sync_env;
+  kp.trace = trace_dev();
+  if (kp.trace) {
+    std::snprintf(tag, sizeof(tag), "%s M%d N%d K%d BN%d st%d %s%s%s ew%d", kp.mode ? "conv" : "lin", kp.M, kp.N, num_kb * kp.BK, kp.BN,
+                  kp.stages, kp.b_resident ? "resident" : "stream", kp.pair ? " pair" : "", kp.halo ? " halo" : te ? " tma-epi" : ts ? " tma-store" : "", ew);
+    kp.serial = trace_launch(tag, grid, threads, smem, s);
+  }
   if (prof_enabled()) {
     std::snprintf(tag, sizeof(tag), "%s M%d N%d K%d BN%d BK%d st%d grid%d %s%s%s", kp.mode ? "conv" : "lin", kp.M, kp.N,
                   num_kb * kp.BK, kp.BN, kp.BK, kp.stages, grid, kp.b_resident ? "resident" : "stream", kp.pair ? " pair" : "",

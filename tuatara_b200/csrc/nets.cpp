@@ -300,12 +300,7 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
   ARENA_GET(logits_ar, float, static_cast<size_t>(R) * NC);
   ARENA_GET(logits, float, static_cast<size_t>(R) * NC);
   ARENA_GET(ids, int, static_cast<size_t>(R));
-  {
-    std::vector<int> init(static_cast<size_t>(R), pd.pad_id);
-    for (int c = 0; c < n; ++c) init[static_cast<size_t>(c) * L] = pd.bos_id;
-    TT_CUDA_TRY(cudaMemcpyAsync(tokens, init.data(), sizeof(int) * R, cudaMemcpyHostToDevice, s));
-    TT_CUDA_TRY(cudaStreamSynchronize(s));  // `init` is stack-owned
-  }
+  RUN(tokens_init(tokens, n, L, pd.bos_id, pd.pad_id, s));
   const float* posq = wf.f32("posq");
   stage_begin(s);
   auto stream_tail = [&](const DecoderStep& st, int rows, float* logits_dst, int ldl) -> cudaError_t {
@@ -354,6 +349,7 @@ DeviceWeights::~DeviceWeights() {
 DeviceCtx::~DeviceCtx() {
   cudaSetDevice(device);
   post_workspace_free(&post);
+  if (patch_buf) cudaFree(patch_buf);
   if (pinned) cudaFreeHost(pinned);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -397,7 +393,7 @@ cudaError_t DeviceCtx::init(const std::string& dir, std::shared_ptr<DeviceWeight
   RUN(layernorm(wf.f32("posq"), pd.L, pd.D, wf.f32("dec.nq.g"), wf.f32("dec.nq.b"), 1e-5f, qn, nullptr, 0, stream));
   RUN(lin(stream, qn, pd.D, pd.L, pd.D, wf.bf("dec.sa.in.w"), pd.D, wf.f32("dec.sa.in.b"), ACT_NONE, nullptr,
           RES_NONE, 0, 0, w->q_sa_table, OUT_F32, pd.D));
-  TT_CUDA_TRY(cudaStreamSynchronize(stream));
+  TT_CUDA_TRY(stream_sync(stream));
   return cudaSuccess;
 }
 

@@ -9,6 +9,7 @@
 #include "common.h"
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
+#include "trace.h"
 
 namespace tt {
 
@@ -166,7 +167,8 @@ struct AttnCtl {
 constexpr int kAttnSmem = 3 * 16384 + 1024 + 64;
 
 __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtensorMap tm_qkv,
-                                                  __nv_bfloat16* __restrict__ out, int D, float scale_log2e) {
+                                                  __nv_bfloat16* __restrict__ out, int D, float scale_log2e,
+                                                  uint32_t* trace, uint32_t serial) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtens
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform: warp 0 issues through the uniform datapath
 
   if (tid == 0) {
+    trace_small(trace, serial, TR_ENTER);
     ptx::prefetch_tmap(&tm_qkv);
     ptx::mbar_init(&ctl->bar_load, 1);
     ptx::mbar_init(&ctl->bar_s, 1);
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtens
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+  if (tid == 0) { trace_small(trace, serial, TR_ALLOC); trace_tmem_event(trace, serial, blockIdx.y * gridDim.x + blockIdx.x, 1); }
 
   if (warp == 0) {  // all 32 lanes converged, one elected lane issues (ptx.cuh "_e" wrappers)
     ptx::mbar_arrive_expect_tx_e(&ctl->bar_load, 3 * 16384);
@@ -286,6 +290,7 @@ __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtens
   if (warp == 0) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, 128);
+    if (tid == 0) { trace_small(trace, serial, TR_DONE); trace_tmem_event(trace, serial, blockIdx.y * gridDim.x + blockIdx.x, 2); }
   }
 }
 
@@ -699,7 +704,9 @@ cudaError_t attention_enc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int crop
   if (!make_tmap_bf16(&tm, qkv, 2, dims, strides, box, 128)) return cudaErrorInvalidValue;
   TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(k_attn_enc), kAttnSmem));
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
-  k_attn_enc<<<dim3(heads, crops), 128, kAttnSmem, s>>>(tm, out, D, scale_log2e);
+  uint32_t* const trace = trace_dev();
+  const uint32_t serial = trace ? trace_launch("k_attn_enc", 0 /* tracked per SM slot, not per CTA */, 128, kAttnSmem, s) : 0;
+  k_attn_enc<<<dim3(heads, crops), 128, kAttnSmem, s>>>(tm, out, D, scale_log2e, trace, serial);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -740,6 +747,18 @@ cudaError_t dec_cross_attn(const DecoderStep& st, const __nv_bfloat16* q, const 
     return cudaSuccess;
   }
   k_dec_cross_attn<<<dim3(st.np, st.n_crops), 384, 0, s>>>(st, q, mem_kv, out);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+// tokens[crop][0] = bos, the rest pad: the AR context before the first step (upstream PARSeq forward(): tgt_in)
+__global__ void k_tokens_init(int* __restrict__ tokens, int n, int L, int bos, int pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * L) tokens[i] = (i % L == 0) ? bos : pad;
+}
+cudaError_t tokens_init(int* tokens, int n, int L, int bos, int pad, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_tokens_init<<<(n * L + 255) / 256, 256, 0, s>>>(tokens, n, L, bos, pad);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }
