@@ -6,9 +6,10 @@ synthetic 1280x1280 pages, 1/2/4/8 GPUs).
     python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
 
 One process per GPU (torchrun sets RANK / LOCAL_RANK / WORLD_SIZE for N > 1).  A *step* is one pass
-of the whole path (CRAFT -> post-process -> crop/resize -> PARSeq -> decode) over this rank's batch
-of synthetic pages; pages are independent, so ranks share nothing (weak scaling, no collective on
-the data path; torch.distributed is used only for the barrier and the max-over-ranks of the time).
+of the whole path (CRAFT -> post-process -> crop/resize -> PARSeq -> decode) over BASELINE configs[4]'s
+batch of 512 synthetic pages, rank r owning pages [r*512/N, (r+1)*512/N) (strong scaling; pages are
+independent, so ranks share nothing: no collective on the data path, torch.distributed is used only
+for the barrier and the max-over-ranks of the time).
 
 Workload: uint8 1280x1280x3 pages, 300 words each, reference defaults
 (canvas 1024 -> CRAFT input 1024^2 -> 512^2 score maps).  Random-init weights give near-constant
@@ -236,7 +237,7 @@ def run_reference(args, rank, world):
 
 # ------------------------------------------------------------------ multi-rank host logic
 def rank_page_indices(rank: int, pages_per_gpu: int) -> list[int]:
-    """Pages are independent units: rank r owns pages [r*n, (r+1)*n) of the synthetic set (weak scaling)."""
+    """Pages are independent units: rank r owns pages [r*n, (r+1)*n) of the synthetic set."""
     return list(range(rank * pages_per_gpu, (rank + 1) * pages_per_gpu))
 
 
@@ -279,34 +280,39 @@ def run_native(args, rank, local_rank, world):
     wdir = ensure_weights()
     cfg = tb.default_config()
     cfg.max_batch_pages = args.batch_pages
-    cfg.slots_per_gpu = env_int("TT_SLOTS", 2)  # two execution slots per GPU (the library default is one)
+    cfg.slots_per_gpu = env_int("TT_SLOTS", 2)  # two execution slots per GPU (the library default)
     eng = tb.Engine(wdir, devices=[local_rank], cfg=cfg)
     stream = torch.cuda.ExternalStream(lib.tt_engine_stream(eng._h, 0), device=torch.device("cuda", local_rank))
 
-    n = args.pages_per_gpu
+    n = args.pages_per_gpu if args.pages_per_gpu > 0 else max(1, args.total_pages // world)
     mine = rank_page_indices(rank, n)
-    pages_np = [synth.synth_page(i) for i in mine]
-    maps_np = [synth.synth_score_maps(i) for i in mine]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(min(16, os.cpu_count() or 4)) as ex:   # 512 distinct pages + maps: ~45 s single-threaded
+        pages_np = list(ex.map(synth.synth_page, mine))
+        maps_np = list(ex.map(synth.synth_score_maps, mine))
     pages_dev = [torch.from_numpy(p).cuda() for p in pages_np]
     maps_dev = [torch.from_numpy(m).cuda() for m in maps_np]
     pages_pin = [torch.from_numpy(p).pin_memory() for p in pages_np]
 
-    def make_call(tensors, on_dev):
-        arr = (_native.tt_image * n)(*[_native.tt_image(t.data_ptr(), PAGE, PAGE, 3, PAGE * 3) for t in tensors])
-        ptrs = (C.c_void_p * n)(*[m.data_ptr() for m in maps_dev])
-        opt = _native.tt_ocr_options(int(on_dev), 1, ptrs)
+    def make_call(tensors, maps, on_dev, engine=None, detect_only=False):
+        """One tt_ocr_pages_ex call over `tensors` (torch uint8 [H,W,3], device or pinned host) with device score maps."""
+        k = len(tensors)
+        arr = (_native.tt_image * k)(*[_native.tt_image(t.data_ptr(), t.shape[0], t.shape[1], 3, t.shape[1] * 3) for t in tensors])
+        ptrs = (C.c_void_p * k)(*[m.data_ptr() for m in maps])
+        opt = _native.tt_ocr_options(int(on_dev), 1, ptrs, int(detect_only))
+        h = (engine or eng)._h
 
         def call():
             res = C.POINTER(_native.tt_result)()
-            tb.check(lib.tt_ocr_pages_ex(eng._h, arr, n, C.byref(opt), C.byref(res)), "tt_ocr_pages_ex")
+            tb.check(lib.tt_ocr_pages_ex(h, arr, k, C.byref(opt), C.byref(res)), "tt_ocr_pages_ex")
             items = sum(res.contents.pages[i].n_items for i in range(res.contents.n_pages))
             lib.tt_result_free(res)
             return items
-        call.keep = (arr, ptrs, opt)
+        call.keep = (arr, ptrs, opt, tensors, maps)
         return call
 
-    step_dev = make_call(pages_dev, True)
-    step_host = make_call(pages_pin, False)
+    step_dev = make_call(pages_dev, maps_dev, True)
+    step_host = make_call(pages_pin, maps_dev, False)
 
     def barrier():
         if world > 1:
@@ -361,7 +367,8 @@ def run_native(args, rank, local_rank, world):
     r_host = timed(step_host, args.steps)                  # same through host buffers
     lib.tt_engine_set_slots(eng._h, 1)                     # roofline pass: one slot => kernels strictly serial, so the
     step_dev()                                             # per-launch CUDA events measure each launch alone
-    r_prof = timed(step_dev, args.steps, profile=True)
+    prof_steps = min(args.steps, 2)
+    r_prof = timed(step_dev, prof_steps, profile=True)
     lib.tt_engine_set_slots(eng._h, env_int("TT_SLOTS", 2))
 
     peaks = measured_peaks()
@@ -393,7 +400,7 @@ def run_native(args, rank, local_rank, world):
             continue
         tf, gbs = st["flops"] / sec / 1e12, st["bytes"] / sec / 1e9
         bound = "tensor" if name in ("craft", "parseq_encoder") else "hbm"
-        ent = {"ms_per_step": st["ms"], "share_of_serial_step": st["ms"] / (r_prof["ms"] / args.steps), "bound": bound}
+        ent = {"ms_per_step": st["ms"], "share_of_serial_step": st["ms"] / (r_prof["ms"] / prof_steps), "bound": bound}
         if st["flops"] > 0:
             ent.update(tflops=tf, frac_tensor=tf / peaks["tf_sustained"])
         if st["bytes"] > 0:
@@ -402,13 +409,14 @@ def run_native(args, rank, local_rank, world):
     achieved = pf / (pm / 1e3) / 1e12 if pm > 0 else 0.0
     line = {
         "metric": "pages/sec end-to-end", "value": value, "unit": "pages/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": r_dev["ms"] / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": r_dev["ms"] / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.pages_per_gpu <= 0 else "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "configs[4]: synthetic 1280x1280 pages end-to-end, 300 words/page, reference defaults "
-                               "(canvas 1024), CRAFT output overridden by the page's synthetic score map after CRAFT ran",
-                   "pages_per_gpu_per_step": n, "group_pages": args.batch_pages, "craft_batch_pages": min(8, args.batch_pages), "crops_per_page": WORDS,
+        "config": {"workload": f"configs[4]: batch of {n * world} synthetic 1280x1280 pages end-to-end, 300 words/page, reference "
+                               "defaults (canvas 1024), CRAFT output overridden by the page's synthetic score map after CRAFT ran",
+                   "pages_per_step": n * world, "pages_per_gpu_per_step": n, "group_pages": args.batch_pages, "craft_batch_pages": min(8, args.batch_pages), "crops_per_page": WORDS,
                    "weights": "seeded random init (CRAFT VGG16-BN, PARSeq-base)", "parallelism": f"dp{world} (pages)",
-                   "slots_per_gpu": env_int("TT_SLOTS", 2),
+                   "slots_per_gpu": env_int("TT_SLOTS", 2), "work_queue": "detection units of <= 8 pages pulled by the slots; crops of all sizes share PARSeq batches",
                    "kernel_paths": "conservative (retry after a failed first attempt)" if os.environ.get("TT_BENCH_RETRY") else "default",
                    "l2": f"inputs larger than L2: {n * PAGE * PAGE * 3 / 2**20:.0f} MiB of distinct pages per step"},
         "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": r_host["h2d"], "d2h_bytes_per_step": r_host["d2h"],
@@ -418,8 +426,8 @@ def run_native(args, rank, local_rank, world):
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)",
                      "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tf_sustained"], "traffic": gemm_traffic(), "peak_source": peaks["source"],
-                     "launches": int(pl), "kernel_ms_per_step": pm / args.steps,
-                     "kernel_share_of_step": pm / r_prof["ms"], "serial_ms_per_step": r_prof["ms"] / args.steps,
+                     "launches": int(pl), "kernel_ms_per_step": pm / prof_steps,
+                     "kernel_share_of_step": pm / r_prof["ms"], "serial_ms_per_step": r_prof["ms"] / prof_steps,
                      "note": "per-launch events from an extra timed pass with one execution slot (serial kernels); "
                              "the headline value runs two slots per GPU",
                      "algorithmic_gflop_per_step": n * (CRAFT_GFLOP_PER_PAGE + WORDS * PARSEQ_GFLOP_PER_CROP)},
@@ -428,6 +436,20 @@ def run_native(args, rank, local_rank, world):
                    "note": "configs[2]: 1024 synthetic 32x128 crops, PARSeq-base, 26 AR steps + refinement, host u8 crops in / ids out "
                            "(wall clock around tt_parseq_forward, this rank)"},
     }
+    if rank == 0 and not args.no_configs:
+        line["configs"] = other_configs(tb, lib, eng, make_call, torch)
+    if world >= 2 and not args.no_configs:
+        # the engine's OWN multi-GPU path (one engine over two devices, units pulled from the shared queue by both):
+        # rank 0 checks it against its single-device engine on the same pages
+        if rank == 0:
+            eng2 = tb.Engine(wdir, devices=[0, 1], cfg=cfg)
+            k = min(16, n)
+            want = eng.ocr_pages(pages_np[:k], score_override=maps_np[:k])
+            got = eng2.ocr_pages(pages_np[:k], score_override=maps_np[:k])
+            line["engine_dp_check"] = "ok" if got == want and sum(len(p) for p in got) == k * WORDS else "MISMATCH"
+            line["engine_dp_check_note"] = f"one engine over devices [0,1], {k} pages: identical to the single-device engine"
+            eng2.close()
+        dist.barrier()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, npg, threads = cpu_pipeline_sample(1)
         line["cpu_baseline"] = {"value": npg / sec, "unit": "pages/s", "cores": os.cpu_count(), "kind": "port",
@@ -438,6 +460,50 @@ def run_native(args, rank, local_rank, world):
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(tb, lib, eng, make_call, torch):
+    """BASELINE.json configs #1 (examples/resume.cpp's page), #2 (CRAFT detection only, one 1280^2 page) and #4 (the FUNSD
+    page) through the same C ABI: latency of one image_to_data-style call (host page in, items out, wall clock, median
+    of 15) and pages/s with 64 copies of the page in one call.  Pixels of the reference's fixture PNGs come from
+    tests/golden/fixture_images.npz (decoded once by tests/golden/make_golden_images.py); their score maps are the
+    ink-derived 8-bit maps of the same file, so post-processing, cropping and PARSeq see a realistic word count."""
+    from tuatara_b200 import synth
+
+    fx = np.load(ROOT / "tests" / "golden" / "fixture_images.npz")
+    out = {}
+
+    def measure(key, img, maps_f32, what, detect_only=False):
+        page = torch.from_numpy(np.ascontiguousarray(img)).pin_memory()
+        m = torch.from_numpy(np.ascontiguousarray(maps_f32)).cuda()
+        one = make_call([page], [m], False, detect_only=detect_only)
+        words = one()
+        for _ in range(3):
+            one()
+        lat = []
+        for _ in range(15):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            one()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        many = make_call([page] * 64, [m] * 64, False, detect_only=detect_only)
+        many()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            many()
+        dt = time.perf_counter() - t0
+        out[key] = {"workload": what, "page": f"{img.shape[1]}x{img.shape[0]}", "words": int(words),
+                    "latency_ms": statistics.median(lat), "latency_ms_min": min(lat),
+                    "pages_per_s": reps * 64 / dt, "batch": 64}
+
+    for key, name, what in (("1_resume", "resume_example", "configs[0]: examples/resume.cpp page (images/resume_example.png), CRAFT + PARSeq"),
+                            ("4_funsd", "funsd_0001129658", "configs[3]: FUNSD form page (images/funsd_0001129658.png), end to end")):
+        measure(key, fx[f"{name}.img"], fx[f"{name}.maps_u8"].astype(np.float32) / np.float32(255.0), what)
+    measure("2_craft_only", synth.synth_page(0), synth.synth_score_maps(0),
+            "configs[1]: CRAFT detection only (resize, CRAFT, post-processing, boxes), single 1280x1280 synthetic page", detect_only=True)
+    return out
 
 
 def supervise(args) -> bool:
@@ -481,7 +547,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--pages-per-gpu", type=int, default=64)
+    ap.add_argument("--total-pages", type=int, default=512, help="BASELINE configs[4]: the batch all ranks share (strong scaling)")
+    ap.add_argument("--pages-per-gpu", type=int, default=0, help="> 0: fixed pages per rank instead (weak scaling, development)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs #1/#2/#4 block and the engine_dp_check")
     ap.add_argument("--batch-pages", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -89,3 +89,21 @@ def test_synthetic_page_gives_300_boxes_inside_the_image():
     inv = np.float32(1) / np.float32(0.8)
     boxes = R.adjust_result_coordinates(det, inv, inv)
     assert not any(R.crop_rect((1280, 1280, 3), b)[4] for b in boxes)
+
+
+def test_text_threshold_is_compared_as_float_like_the_reference():
+    """tuatara.cpp:154 `if (maxVal < text_threshold)`: double against the float parameter (0.7f -> 0.699999988...).  A
+    component whose maximum is exactly float32(0.7) is kept; the oracle used to compare against the Python double 0.7
+    and dropped it (round-1 verdict)."""
+    import numpy as np
+    import torch
+    t = np.float32(0.7)
+    m = np.zeros((48, 96, 2), np.float32)
+    m[4:12, 4:24, 0] = 0.5;  m[6, 10, 0] = t
+    m[20:28, 4:24, 0] = 0.5; m[22, 10, 0] = np.nextafter(t, np.float32(0))
+    m[4:12, 60:80, 0] = 1.0
+    m[0, 0, 1], m[0, 1, 1] = 0.0, 1.0
+    det, dbg = R.get_detected_boxes(torch.from_numpy(m[..., 0].copy()), torch.from_numpy(m[..., 1].copy()), 0.7, 0.4, 0.4)
+    kept_rows = sorted(int(round(r[0][1])) for r in det)
+    assert len(det) == 2 and kept_rows[0] < 12, kept_rows   # the float32(0.7) blob (rows 4..11) and the 1.0 blob survive
+    assert float(t) < 0.7   # the whole point: float32(0.7) is below the double 0.7

@@ -71,6 +71,28 @@ def test_postprocess_degenerate(native_lib):
     _post_case(edge)
 
 
+def threshold_edge_maps():
+    """Three blobs whose maxima straddle the `maxVal < text_threshold` test of tuatara.cpp:154: the reference compares the
+    double maxVal with the FLOAT parameter 0.7f (promoted: 0.699999988...), so a maximum of exactly float32(0.7) is kept,
+    one ulp below is dropped.  min 0 / max 1 are pinned so that the min-max normalisation is the identity."""
+    t = np.float32(0.7)
+    m = np.zeros((48, 96, 2), np.float32)
+    m[4:12, 4:24, 0] = 0.5;  m[6, 10, 0] = t                                   # kept: max == float32(0.7)
+    m[20:28, 4:24, 0] = 0.5; m[22, 10, 0] = np.nextafter(t, np.float32(0))      # dropped: one ulp below
+    m[36:44, 4:24, 0] = 0.5; m[38, 10, 0] = np.nextafter(t, np.float32(1))      # kept: one ulp above
+    m[4:12, 60:80, 0] = 1.0                                                     # pins the maximum
+    m[0, 0, 1], m[0, 1, 1] = 0.0, 1.0
+    m[0, 1, 0] = 0.0
+    return m
+
+
+def test_postprocess_text_threshold_float_compare(native_lib):
+    m = threshold_edge_maps()
+    det, dbg = R.get_detected_boxes(torch.from_numpy(m[..., 0].copy()), torch.from_numpy(m[..., 1].copy()), 0.7, 0.4, 0.4)
+    assert len(det) == 3 and dbg.n_labels - 1 >= 4   # 4 text blobs (+ the affinity pin), the one-ulp-below blob is dropped
+    assert _post_case(m) == 3
+
+
 @pytest.mark.parametrize("h,w", [(1280, 1280), (763, 607), (1000, 754), (664, 1245), (206, 275), (2000, 1128),
                                  (1171, 3000), (1024, 1024), (2048, 2048), (31, 57)])
 def test_preprocess_bit_exact(native_lib, h, w):
