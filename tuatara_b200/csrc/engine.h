@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "dec_fused.cuh"
 #include "detect.h"
 #include "postprocess.cuh"
 #include "tuatara_c.h"
@@ -68,6 +69,9 @@ struct DeviceWeights {
   WeightFile craft, parseq;
   ParseqDims pd;
   float* q_sa_table = nullptr;  // [L][D] fp32: self-attn queries of the 26 positions (crop independent)
+  __nv_bfloat16* kv_table = nullptr;  // [L][n_tok][2D] bf16: content-stream K|V of every (position, token) pair
+  float* sc_table = nullptr;    // [L][L][n_tok][dec_heads] fp32: AR self-attention scores as a lookup (nn_kernels.cuh)
+  DecDenseWeights dd;           // tensor maps + vectors of the fused decoder kernels (dec_fused.cu)
   ~DeviceWeights();
 };
 
@@ -79,6 +83,8 @@ constexpr int kSlotsPerDevice = 4;   // upper bound; tt_config.slots_per_gpu pic
 struct DeviceCtx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second half of a recognition batch's AR loop (overlaps the first half's cross attention)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::shared_ptr<DeviceWeights> w;
   Arena arena;
   PostWorkspace post;           // sized lazily for (batch, H, W)

@@ -333,12 +333,15 @@ __global__ void k_dec_context(const int* __restrict__ tokens, const float* __res
 // them with the query.  Values: lane = head dim, loop over the keys with the probabilities broadcast.
 __global__ void k_dec_self_attn(DecoderStep st, const float* __restrict__ q_table,
                                 const __nv_bfloat16* __restrict__ kv, const int* __restrict__ tokens, int eos_id,
-                                __nv_bfloat16* __restrict__ out) {
+                                int n_tok, __nv_bfloat16* __restrict__ out) {
   const int pi = blockIdx.x, crop = blockIdx.y;
   const int p = st.p0 + pi;
   const int head = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int D = st.D, L = st.L;
-  const __nv_bfloat16* kbase = kv + static_cast<long long>(crop) * L * 2 * D + head * 32;
+  // key j of this crop = row (j, tokens[crop][j]) of the content K|V table; lane l keeps row l's offset
+  const int my_tok = lane < L ? tokens[crop * L + lane] : 0;
+  const long long my_row = (static_cast<long long>(lane) * n_tok + my_tok) * 2 * D;
+  const __nv_bfloat16* kbase = kv + head * 32;
   // key j allowed?  AR: j <= p.  refine: j != p+1 and no EOS among tokens[1..j]
   int first_eos = L;  // first j >= 1 with tokens[j] == eos
   if (st.refine) {
@@ -353,11 +356,14 @@ __global__ void k_dec_self_attn(DecoderStep st, const float* __restrict__ q_tabl
   const __nv_bfloat16* vbase = kbase + D + lane;
   __nv_bfloat16 vraw[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) vraw[j] = (j < nkeys) ? vbase[static_cast<long long>(j) * 2 * D] : __float2bfloat16(0.f);
+  for (int j = 0; j < 32; ++j) {
+    const long long row_j = __shfl_sync(0xffffffffu, my_row, j);
+    vraw[j] = (j < nkeys) ? vbase[row_j] : __float2bfloat16(0.f);
+  }
   float score = -INFINITY;
   if (mine) {
     const float4* q4 = reinterpret_cast<const float4*>(q_table + p * D + head * 32);
-    const uint4* k4 = reinterpret_cast<const uint4*>(kbase + static_cast<long long>(lane) * 2 * D);
+    const uint4* k4 = reinterpret_cast<const uint4*>(kbase + my_row);
     float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -378,6 +384,113 @@ __global__ void k_dec_self_attn(DecoderStep st, const float* __restrict__ q_tabl
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc += __shfl_sync(0xffffffffu, pr, j) * __bfloat162float(vraw[j]);  // pr == 0 beyond nkeys
   out[(static_cast<long long>(crop) * st.np + pi) * D + head * 32 + lane] = __float2bfloat16(acc);
+}
+
+// Self-attention scores of the AR pass as a lookup: with the content K|V a function of (position, token) and the
+// queries a function of the position alone, score(i, j, token_j, head) = scale * q_table[i][head] . K[j][token_j][head]
+// is a [L][L][n_tok][heads] fp32 table (3.1 MB for PARSeq-base) computed once per engine.  Same summation order as
+// k_dec_self_attn, so both produce the same bits.
+__global__ void k_dec_score_table(const float* __restrict__ q_table, const __nv_bfloat16* __restrict__ kv_table, int L,
+                                  int n_tok, int D, int heads, float* __restrict__ out) {
+  const long long total = static_cast<long long>(L) * L * n_tok * heads;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int h = static_cast<int>(idx % heads);
+  long long t = idx / heads;
+  const int tok = static_cast<int>(t % n_tok); t /= n_tok;
+  const int j = static_cast<int>(t % L);
+  const int i = static_cast<int>(t / L);
+  const float4* q4 = reinterpret_cast<const float4*>(q_table + i * D + h * 32);
+  const uint4* k4 = reinterpret_cast<const uint4*>(kv_table + (static_cast<long long>(j) * n_tok + tok) * 2 * D + h * 32);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float f[8];
+    unpack8(__ldg(k4 + c), f);
+    const float4 qa = __ldg(q4 + 2 * c), qb = __ldg(q4 + 2 * c + 1);
+    acc += qa.x * f[0] + qa.y * f[1] + qa.z * f[2] + qa.w * f[3] + qb.x * f[4] + qb.y * f[5] + qb.z * f[6] + qb.w * f[7];
+  }
+  out[idx] = acc * 0.17677669529663687f;  // 1/sqrt(32)
+}
+
+// AR-step self attention, one warp per crop (8 crops per block).  Lane j owns key j: it gathers the heads' scores of
+// (step, j, token_j) from the score table (heads * 4 contiguous bytes), the softmax per head runs across the lanes,
+// the probabilities go through a per-warp smem tile, and the V rows (row (j, token_j) of the K|V table, L2 resident)
+// are accumulated with lane = 16-byte chunk of the row: every load is a full coalesced row.
+template <int HEADS>
+__global__ void __launch_bounds__(256) k_dec_self_attn_ar(int n, int D, int L, int step, int n_tok,
+                                                          const float* __restrict__ sc_table,
+                                                          const __nv_bfloat16* __restrict__ kv_table,
+                                                          const int* __restrict__ tokens, __nv_bfloat16* __restrict__ out) {
+  __shared__ float s_p[8][HEADS][32];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crop = blockIdx.x * 8 + wib;
+  if (crop >= n) return;
+  const int nkeys = step + 1;
+  const int tok = lane < nkeys ? tokens[crop * L + lane] : 0;
+  float sc[HEADS];
+  if (lane < nkeys) {
+    const float4* src = reinterpret_cast<const float4*>(sc_table + ((static_cast<long long>(step) * L + lane) * n_tok + tok) * HEADS);
+#pragma unroll
+    for (int h4 = 0; h4 < HEADS / 4; ++h4) {
+      const float4 v = __ldg(src + h4);
+      sc[4 * h4] = v.x; sc[4 * h4 + 1] = v.y; sc[4 * h4 + 2] = v.z; sc[4 * h4 + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int h = 0; h < HEADS; ++h) sc[h] = -INFINITY;
+  }
+#pragma unroll
+  for (int h = 0; h < HEADS; ++h) {
+    float mx = sc[h];
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = lane < nkeys ? __expf(sc[h] - mx) : 0.f;
+    float sum = e;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    s_p[wib][h][lane] = e / sum;
+  }
+  __syncwarp();
+  // V accumulation: chunk c (8 dims) belongs to head c / 4
+  const int chunks = D / 8;                       // 48 (base) / 24 (tiny): lanes take chunk `lane` and `lane + 32`
+  const bool two = lane + 32 < chunks;
+  const bool one = lane < chunks;
+  const int h0 = lane >> 2, h1 = (lane + 32) >> 2;
+  float a0[8], a1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a0[e] = 0.f; a1[e] = 0.f; }
+  const __nv_bfloat16* vbase = kv_table + D;
+  for (int j0 = 0; j0 < nkeys; j0 += 4) {
+    uint4 u0[4], u1[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j0 + jj;
+      const int tj = __shfl_sync(0xffffffffu, tok, j & 31);
+      const uint4* row = reinterpret_cast<const uint4*>(vbase + (static_cast<long long>(j) * n_tok + tj) * 2 * D);
+      u0[jj] = (j < nkeys && one) ? __ldg(row + lane) : make_uint4(0u, 0u, 0u, 0u);
+      u1[jj] = (j < nkeys && two) ? __ldg(row + lane + 32) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j0 + jj;
+      if (j >= nkeys) break;
+      float f[8];
+      if (one) {
+        const float pa = s_p[wib][h0][j];
+        unpack8(u0[jj], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a0[e] += pa * f[e];
+      }
+      if (two) {
+        const float pb = s_p[wib][h1][j];
+        unpack8(u1[jj], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a1[e] += pb * f[e];
+      }
+    }
+  }
+  __nv_bfloat16* orow = out + static_cast<long long>(crop) * D;
+  if (one) st8(orow + lane * 8, pack8(a0));
+  if (two) st8(orow + (lane + 32) * 8, pack8(a1));
 }
 
 // Decoder cross-attention over the 128 memory tokens of a crop.  grid (np, crops), 12 warps (= heads).
@@ -477,14 +590,15 @@ constexpr int kRefPitch = 136;  // bf16 elements per staged row (128 + 8 pad)
 template <int KEYS, bool SELF>
 __global__ void __launch_bounds__(128) k_dec_attn_refine(const void* __restrict__ q_in, const __nv_bfloat16* __restrict__ kv,
                                                          int nkeys, int np, const int* __restrict__ tokens, int eos_id,
-                                                         int L, __nv_bfloat16* __restrict__ out) {
+                                                         int L, int n_tok, __nv_bfloat16* __restrict__ out) {
   constexpr int kD = 384, kNT = KEYS / 8, kKS = KEYS / 16;
   extern __shared__ __align__(16) uint8_t ref_smem[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(ref_smem);
   __nv_bfloat16* sV = sK + KEYS * kRefPitch;
   const int hg = blockIdx.x, crop = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const __nv_bfloat16* kvb = kv + static_cast<long long>(crop) * nkeys * 2 * kD + hg * 128;
+  // SELF: key row j = row (j, tokens[crop][j]) of the content K|V table; cross attention: the crop's memory rows
+  const __nv_bfloat16* kvb = kv + (SELF ? 0 : static_cast<long long>(crop) * nkeys * 2 * kD) + hg * 128;
   // stage K then V: 16 chunks of 16 B per row
   for (int pass = 0; pass < 2; ++pass) {
     __nv_bfloat16* dst = pass ? sV : sK;
@@ -492,7 +606,8 @@ __global__ void __launch_bounds__(128) k_dec_attn_refine(const void* __restrict_
       const int row = c >> 4, ch = c & 15;
       const uint32_t d = ptx::smem_u32(dst + row * kRefPitch + ch * 8);
       if (row < nkeys) {
-        const __nv_bfloat16* src = kvb + static_cast<long long>(row) * 2 * kD + pass * kD + ch * 8;
+        const long long grow = SELF ? static_cast<long long>(row) * n_tok + tokens[crop * L + row] : row;
+        const __nv_bfloat16* src = kvb + grow * 2 * kD + pass * kD + ch * 8;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
       } else {
         ptx::sts128(d, make_uint4(0u, 0u, 0u, 0u));
@@ -720,17 +835,33 @@ cudaError_t dec_context(const int* tokens, const float* embed, const float* posq
   return cudaSuccess;
 }
 
-cudaError_t dec_self_attn(const DecoderStep& st, const float* q_table, const __nv_bfloat16* kv, const int* tokens,
-                          int eos_id, __nv_bfloat16* out, cudaStream_t s) {
+cudaError_t dec_score_table(const float* q_table, const __nv_bfloat16* kv_table, int L, int n_tok, int D, int heads,
+                            float* out, cudaStream_t s) {
+  if (D != heads * 32) { set_error("dec_score_table: head dim must be 32"); return cudaErrorInvalidValue; }
+  const long long total = static_cast<long long>(L) * L * n_tok * heads;
+  k_dec_score_table<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(q_table, kv_table, L, n_tok, D, heads, out);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t dec_self_attn(const DecoderStep& st, const float* q_table, const float* sc_table, const __nv_bfloat16* kv,
+                          const int* tokens, int eos_id, int n_tok, __nv_bfloat16* out, cudaStream_t s) {
   if (st.n_crops <= 0) return cudaSuccess;
   if (st.D != st.heads * 32 || st.L > 32) { set_error("dec_self_attn: head dim must be 32, L <= 32"); return cudaErrorInvalidValue; }
-  if (st.refine && st.p0 == 0 && st.np == st.L && st.D == 384) {
-    constexpr int smem = 2 * 32 * kRefPitch * 2;
-    k_dec_attn_refine<32, true><<<dim3(3, st.n_crops), 128, smem, s>>>(q_table, kv, st.L, st.np, tokens, eos_id, st.L, out);
+  if (!st.refine && st.np == 1 && sc_table != nullptr && (st.heads == 12 || st.heads == 6) && st.D <= 512) {
+    const int grid = (st.n_crops + 7) / 8;
+    if (st.heads == 12) k_dec_self_attn_ar<12><<<grid, 256, 0, s>>>(st.n_crops, st.D, st.L, st.p0, n_tok, sc_table, kv, tokens, out);
+    else k_dec_self_attn_ar<6><<<grid, 256, 0, s>>>(st.n_crops, st.D, st.L, st.p0, n_tok, sc_table, kv, tokens, out);
     TT_LAUNCH_CHECK();
     return cudaSuccess;
   }
-  k_dec_self_attn<<<dim3(st.np, st.n_crops), st.heads * 32, 0, s>>>(st, q_table, kv, tokens, eos_id, out);
+  if (st.refine && st.p0 == 0 && st.np == st.L && st.D == 384) {
+    constexpr int smem = 2 * 32 * kRefPitch * 2;
+    k_dec_attn_refine<32, true><<<dim3(3, st.n_crops), 128, smem, s>>>(q_table, kv, st.L, st.np, tokens, eos_id, st.L, n_tok, out);
+    TT_LAUNCH_CHECK();
+    return cudaSuccess;
+  }
+  k_dec_self_attn<<<dim3(st.np, st.n_crops), st.heads * 32, 0, s>>>(st, q_table, kv, tokens, eos_id, n_tok, out);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -742,7 +873,7 @@ cudaError_t dec_cross_attn(const DecoderStep& st, const __nv_bfloat16* q, const 
   if (st.np > 1 && st.np <= 32) {
     constexpr int smem = 2 * 128 * kRefPitch * 2;
     TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(k_dec_attn_refine<128, false>), smem));
-    k_dec_attn_refine<128, false><<<dim3(3, st.n_crops), 128, smem, s>>>(q, mem_kv, 128, st.np, nullptr, 0, st.L, out);
+    k_dec_attn_refine<128, false><<<dim3(3, st.n_crops), 128, smem, s>>>(q, mem_kv, 128, st.np, nullptr, 0, st.L, 0, out);
     TT_LAUNCH_CHECK();
     return cudaSuccess;
   }

@@ -36,11 +36,16 @@ struct DecoderStep {
 // content embedding of position `pos` (bos at 0, else pos_queries[pos-1] + sqrt(D)*E[tok]) -> LN_c -> bf16 [n][D]
 cudaError_t dec_context(const int* tokens, const float* embed, const float* posq, const float* g, const float* b,
                         float eps, int pos, int n_crops, int D, int L, __nv_bfloat16* out, cudaStream_t s);
-// self attention of the query stream over the cached content K/V.
-//   q_table fp32 [L][D] (already projected, crop independent), kv_cache bf16 [n][L][2D] (K | V),
-//   tokens int32 [n][L] (for the padding mask), out bf16 [n*np][D].
-cudaError_t dec_self_attn(const DecoderStep& st, const float* q_table, const __nv_bfloat16* kv_cache,
-                          const int* tokens, int eos_id, __nv_bfloat16* out, cudaStream_t s);
+// self attention of the query stream over the content K/V.  With one decoder layer the content stream's K|V at
+//   position j depend only on (j, token): kv_table bf16 [L][n_tok][2D] (K | V) is built once per engine
+//   (DeviceCtx::init) and key j of a crop is row (j, tokens[crop][j]) -- no per-crop cache, no per-step K/V GEMM.
+//   q_table fp32 [L][D] (already projected, crop independent), tokens int32 [n][L], out bf16 [n*np][D].
+//   sc_table fp32 [L][L][n_tok][heads] (nullable): the AR pass's scores as a lookup, see dec_score_table.
+cudaError_t dec_self_attn(const DecoderStep& st, const float* q_table, const float* sc_table, const __nv_bfloat16* kv_table,
+                          const int* tokens, int eos_id, int n_tok, __nv_bfloat16* out, cudaStream_t s);
+// sc_table[i][j][token][head] = q_table[i][head] . K(j, token)[head] / sqrt(32)   (built once per engine)
+cudaError_t dec_score_table(const float* q_table, const __nv_bfloat16* kv_table, int L, int n_tok, int D, int heads,
+                            float* out, cudaStream_t s);
 // cross attention over the encoder memory: q bf16 [n*np][D], mem_kv bf16 [n][128][2D] -> out bf16 [n*np][D]
 cudaError_t dec_cross_attn(const DecoderStep& st, const __nv_bfloat16* q, const __nv_bfloat16* mem_kv,
                            __nv_bfloat16* out, cudaStream_t s);
