@@ -170,6 +170,12 @@ TT_API int tt_rect_to_bbox(const float rect[5], float bbox_out[4]);
 TT_API int tt_linear_dev(const void* A, int lda, int M, int K, const void* W, int N, const float* bias, int act,
                   const void* residual, int res_f32, int ldr, void* out, int out_f32, int ldc, int BN, int resident,
                   void* stream);
+/* Kernel test of the fused LayerNorm pair the PARSeq encoder runs (x += A W1^T + b1; y = act(Linear(LN(x)))):
+ * X fp32 [M][D] in/out, XB bf16 [M][D] out, stats fp32 [M][8] scratch, W2f = W2 * gamma (bf16 [N2][D]),
+ * c0[n] = b2[n] + beta . W2[n], c1[n] = sum_k W2f[n][k]; out bf16 [M][N2].  All device pointers. */
+TT_API int tt_linear_ln_pair_dev(const void* A, int M, int K1, const void* W1, const float* b1, int D, float* X, void* XB,
+                          float* stats, const void* W2f, const float* c0, const float* c1, int N2, int act, float eps,
+                          void* out, void* stream);
 /* NHWC bf16 stride-1 "same" convolution as implicit GEMM; src1 may be NULL (else channel concat).
  * weight bf16 [Cout][taps][C0+C1]; out bf16 [batch][H][W][Cout]. */
 TT_API int tt_conv_dev(const void* src0, int C0, const void* src1, int C1, int batch, int H, int W, int taps, int dil,

@@ -177,3 +177,44 @@ def test_conv_halo(native_lib, B, H, W, C0, Cout):
     nine taps (the tap's A operand is that tile read at a pixel offset); borders, odd sizes, 1 and 2 channel blocks."""
     out, ref = _conv(native_lib, B, H, W, C0, 0, Cout, 9, 1)
     _check(out.reshape(-1, Cout), ref.reshape(-1, Cout), 9 * C0, f"halo conv {B}x{H}x{W} C{C0}->{Cout}")
+
+
+@pytest.mark.parametrize("M,K1,N2,act", [(307200 // 8, 384, 1152, 0), (40000, 1536, 1536, 2), (1000, 96, 768, 0), (129, 384, 1536, 2),
+                                          (128 * 300, 384, 768, 0)])
+def test_linear_layernorm_fused_pair(native_lib, M, K1, N2, act):
+    """LayerNorm fused away (gemm_tc.cuh Epilogue::ln_*): the residual GEMM emits bf16(x) and the rows' (sum, sum of
+    squares), the next GEMM applies (mean, rstd) to its accumulators.  Reference: fp32 LayerNorm + Linear in torch.
+    Sizes cover the GPU-filling and the small-launch regime, a ragged last tile and the K=96 patch-embedding shape."""
+    from tuatara_b200._native import check
+
+    D = 384
+    g = torch.Generator(device="cpu").manual_seed(M + N2)
+    A = (torch.randn(M, K1, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    W1 = (torch.randn(D, K1, generator=g) * 0.05).to(torch.bfloat16).cuda()
+    b1 = torch.randn(D, generator=g).float().cuda() * 0.1
+    X0 = (torch.randn(M, D, generator=g) * 1.5 + 0.3).float().cuda()  # residual stream with a non-zero mean
+    gamma = (1.0 + 0.2 * (torch.rand(D, generator=g) - 0.5)).cuda()
+    beta = (0.05 * torch.randn(D, generator=g)).cuda()
+    W2 = (torch.randn(N2, D, generator=g) * 0.05).cuda()
+    b2 = (torch.randn(N2, generator=g) * 0.02).cuda()
+    W2f = (W2 * gamma[None, :]).to(torch.bfloat16)
+    c1 = W2f.double().sum(1).float()
+    c0 = (b2.double() + W2.double() @ beta.double()).float()
+    X = X0.clone()
+    XB = torch.full((M, D), float("nan"), dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(M, 8, device="cuda")
+    out = torch.full((M, N2), float("nan"), dtype=torch.bfloat16, device="cuda")
+    check(native_lib.tt_linear_ln_pair_dev(A.data_ptr(), M, K1, W1.data_ptr(), b1.data_ptr(), D, X.data_ptr(), XB.data_ptr(),
+                                           stats.data_ptr(), W2f.data_ptr(), c0.data_ptr(), c1.data_ptr(), N2, act, 1e-6,
+                                           out.data_ptr(), None), "tt_linear_ln_pair_dev")
+    torch.cuda.synchronize()
+    x_ref = X0 + A.float() @ W1.float().t() + b1
+    _check(X.cpu(), x_ref.cpu(), K1, "residual stream")
+    assert torch.equal(XB.float(), X.to(torch.bfloat16).float()), "bf16 copy of x"
+    y = torch.nn.functional.layer_norm(X, (D,), gamma, beta, 1e-6) @ W2.t() + b2   # from the kernel's own x: isolates the LN + GEMM
+    if act == 2:
+        y = torch.nn.functional.gelu(y)
+    err = (out.float() - y).norm() / y.norm()
+    print("LN-fused pair rel-L2", float(err))
+    assert torch.isfinite(out.float()).all()
+    assert float(err) <= 6e-3, float(err)

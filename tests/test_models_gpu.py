@@ -141,6 +141,24 @@ def test_parseq_fused_decoder_matches_unfused(engine, monkeypatch):
         assert same.mean() >= 0.95
 
 
+def test_parseq_encoder_layernorm_fusion_matches_unfused(engine, monkeypatch):
+    """Encoder with LayerNorm folded into the GEMM epilogues (default) against the standalone LayerNorm kernel
+    (TT_ENC_LNFUSE=0), same forced AR context: logits agree to bf16 noise, clear decisions are identical."""
+    crops = _crops(200, seed=7)
+    _, id0 = engine.parseq_forward(crops)
+    forced = np.ascontiguousarray(id0[:, :25]).astype(np.int32)
+    lf, idf = engine.parseq_forward(crops, forced)
+    monkeypatch.setenv("TT_ENC_LNFUSE", "0")
+    lu, idu = engine.parseq_forward(crops, forced)
+    monkeypatch.delenv("TT_ENC_LNFUSE")
+    err = _rel_l2(lf, lu)
+    top2 = np.sort(lu, -1)[..., -2:]
+    clear = (top2[..., 1] - top2[..., 0]) > 0.5
+    print("LN-fused vs unfused encoder: logits rel-L2", err, "ids equal", float((idf == idu).mean()))
+    assert 0 < err <= 1e-2, err
+    assert (idf[clear] == idu[clear]).all()
+
+
 def test_decode_matches_reference_tokenizer(native_lib):
     rng = np.random.default_rng(0)
     tok = R.Tokenizer()

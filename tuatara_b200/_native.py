@@ -87,6 +87,7 @@ SIGNATURES = {
     "tt_adjust_rect": (_I, [_P, _F, _F, _F, _P]),
     "tt_rect_to_bbox": (_I, [_P, _P]),
     "tt_linear_dev": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _P]),
+    "tt_linear_ln_pair_dev": (_I, [_P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, C.c_float, _P, _P]),
     "tt_conv_dev": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _I, _P]),
     "tt_postprocess_dev": (_I, [_P, _P, _I, _I, _I, _PI, _P]),
 }

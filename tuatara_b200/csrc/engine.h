@@ -32,6 +32,7 @@ class WeightFile {
   ~WeightFile();
   bool load(const std::string& path, std::vector<int>* meta_out = nullptr);
   const WTensor& get(const std::string& name) const;  // throws std::runtime_error when missing
+  bool has(const std::string& name) const { return t_.find(name) != t_.end(); }
   const __nv_bfloat16* bf(const std::string& name) const { return static_cast<const __nv_bfloat16*>(get(name).ptr); }
   const float* f32(const std::string& name) const { return static_cast<const float*>(get(name).ptr); }
 

@@ -53,12 +53,14 @@ constexpr int kHaloRows = 18;                                // tile height 16 +
 constexpr int kHaloPixels = kHaloRows * kHaloPitch;           // x 128 B (64 channels) = 36 KB, x 64 B (32 channels) = 18 KB
 constexpr int kHaloResidentMax = 82 * 1024;                  // weights that leave room for 3 halo stages in one CTA
 constexpr int kResSlots = 4;
-constexpr int kResSlotBytes = 128 * 128;
+constexpr int kResSlotBytes = 128 * 128;    // fp32 chunk [128 rows][32 cols]
+constexpr int kLnCopyBytes = 4 * 2 * 2048;  // LayerNorm-statistics producer: two 2 KB bf16 store tiles per epilogue warp
 
 struct KParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
   CUtensorMap tmR, tmC;  // TMA epilogue: fp32 residual (load) and output (store), box {32 cols, 128 rows}
+  CUtensorMap tmCb;      // LayerNorm-statistics producer: bf16 copy of the output, box {32 cols, 32 rows}, SWIZZLE_64B
   int mode;  // 0 plain rows, 1 conv tiles
   int M, N, BN, BK;
   int kb_src[2];
@@ -89,6 +91,7 @@ struct alignas(16) SmemCtl {
   uint32_t tmem_base;
   float tail[16 * 16 + 16 + 2 * 16 + 2];
   alignas(16) float bias[2][256];  // the tile's bias row, staged per accumulator stage (broadcast reads in the epilogue)
+  alignas(16) float c1[2][256];    // LayerNorm consumer: the tile's c1 row (see Epilogue::ln_c1)
 };
 
 // Tile schedule shared by the three warp roles.  Streaming mode: tiles round-robin over CTAs with the
@@ -134,9 +137,13 @@ __device__ __forceinline__ long long dbg_clock(bool on) { return on ? clock64() 
 // SWIZZLE_64B smem tile and one lane hands it to a TMA store -- no read-back, no per-thread global stores (the LSU
 // store path cost ~1000 cycles per 128 x 256 tile, profiles/r1b_gemm_roles.md).  Image edges / short last tiles
 // are clipped by the TMA unit.
-template <int OUT, int ACT, bool RES, bool PAIR, int EW, bool TE = false, bool TS = false>
+// LN: LayerNorm fused away (Epilogue::ln_*).  With TE the kernel is the producer (row statistics + bf16 copy of its
+// output), with bf16 outputs it is the consumer (normalisation applied algebraically to the accumulators).
+template <int OUT, int ACT, bool RES, bool PAIR, int EW, bool TE = false, bool TS = false, bool LN = false>
 __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kernel(const __grid_constant__ KParams p) {
   static_assert(!TE || (OUT == OUT_F32 && RES && EW == 4), "TMA epilogue: fp32 out + residual, 4 epilogue warps");
+  static_assert(!LN || TE || OUT == OUT_BF16, "LayerNorm fusion: TMA-epilogue producer or bf16-output consumer");
+  constexpr int kSlot = kResSlotBytes;   // stride of the TMA-epilogue ring
   static_assert(!TS || (OUT == OUT_BF16 && !RES && !TE), "TMA store epilogue: bf16 outputs");
   constexpr int kTsBufs = EW == 16 ? 1 : 2;         // 2 KB store tiles per warp (ping-pong with 8 warps)
   constexpr int kThreads = 64 + 32 * EW + (TE ? 64 : 0);
@@ -158,7 +165,9 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
   uint8_t* sBres = smem;                                        // [num_kb][BN rows] when resident
   uint8_t* ring = smem + (resident ? num_kb * b_bytes : 0);
   uint8_t* res_ring = ring + p.stages * stage_bytes;            // TE only
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(res_ring + (TE ? kResSlots * kResSlotBytes : TS ? EW * kTsBufs * 2048 : 0));
+  uint8_t* ln_copy = res_ring + kResSlots * kSlot;               // TE && LN only
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(res_ring + (TE ? kResSlots * kSlot + (LN ? kLnCopyBytes : 0) : TS ? EW * kTsBufs * 2048 : 0));
+  (void)ln_copy;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -181,6 +190,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
     if constexpr (TE) {
       ptx::prefetch_tmap(&p.tmR);
       ptx::prefetch_tmap(&p.tmC);
+      if constexpr (LN) ptx::prefetch_tmap(&p.tmCb);
       for (int s = 0; s < kResSlots; ++s) {
         ptx::mbar_init(&ctl->res_full[s], 1);
         ptx::mbar_init(&ctl->res_empty[s], 1);
@@ -374,7 +384,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
           ptx::mbar_wait(&ctl->res_empty[slot], ph ^ 1); __syncwarp();
           ptx::mbar_arrive_expect_tx_e(&ctl->res_full[slot], kResSlotBytes);
           // a pair's second tile may not exist, columns may end before the tile does: out-of-bounds parts arrive as zeros
-          ptx::tma_load_2d_e(res_ring + slot * kResSlotBytes, &p.tmR, &ctl->res_full[slot], n0 + c * 32, rrow);
+          ptx::tma_load_2d_e(res_ring + slot * kSlot, &p.tmR, &ctl->res_full[slot], n0 + c * 32, rrow);
           if (++slot == kResSlots) { slot = 0; ph ^= 1; }
         }
       }
@@ -389,7 +399,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
         const int n0 = it.n_tile(p) * p.BN, m0 = m_tile * kBlockM;
         for (int c = 0; c < p.BN / 32; ++c) {
           ptx::mbar_wait(&ctl->chunk_done[slot], ph); __syncwarp();
-          if ((p.debug & 3) == 0) ptx::tma_store_2d_e(&p.tmC, res_ring + slot * kResSlotBytes, n0 + c * 32, m0);  // rows/cols past the tensor are clipped
+          if ((p.debug & 3) == 0) ptx::tma_store_2d_e(&p.tmC, res_ring + slot * kSlot, n0 + c * 32, m0);  // rows/cols past the tensor are clipped
           ptx::bulk_commit_e();
           if (prev >= 0) {
             if (ptx::elect_one()) ptx::bulk_wait_read<1>();   // the previous chunk's store has finished reading its slot
@@ -464,30 +474,69 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
     // NEXT tile is fetched while this one is processed (its LDG latency was 9% of the samples after that).
     const int bias_t = threadIdx.x - 32 * kEpiWarp0;  // 0 .. 32*EW-1 over the epilogue warps
     constexpr int kBiasPer = (256 + 32 * EW - 1) / (32 * EW);  // bias columns per epilogue thread (BN <= 256)
-    auto bias_fetch = [&](const TileIter& t, float (&b)[kBiasPer]) {
+    constexpr bool kLNA = LN && !TE;   // LayerNorm consumer
+    const float* const c1_g = p.epi.ln_c1;
+    auto bias_fetch = [&](const TileIter& t, float (&b)[kBiasPer], float (&c)[kBiasPer]) {
 #pragma unroll
       for (int i = 0; i < kBiasPer; ++i) {
         const int tc = bias_t + i * 32 * EW, col = t.n_tile(p) * BN + tc;
-        b[i] = (t.valid() && bias_g != nullptr && tc < BN && col < N) ? __ldg(bias_g + col) : 0.f;
+        const bool ok = t.valid() && tc < BN && col < N;
+        b[i] = (ok && bias_g != nullptr) ? __ldg(bias_g + col) : 0.f;
+        if constexpr (kLNA) c[i] = ok ? __ldg(c1_g + col) : 0.f;
       }
     };
     TileIter it(p);
-    float bias_cur[kBiasPer];
-    bias_fetch(it, bias_cur);
-    int te_slot = 0;
+    float bias_cur[kBiasPer], c1_cur[kBiasPer];
+    bias_fetch(it, bias_cur, c1_cur);
+    // LayerNorm consumer: (sum, sum of squares) of this thread's row in tile t, summed over the producer's partials
+    float ln_s1n = 0.f, ln_s2n = 0.f;
+    auto ln_fetch = [&](const TileIter& t, float& s1, float& s2) {
+      s1 = 0.f; s2 = 0.f;
+      if constexpr (kLNA) {
+        if (t.valid()) {
+          const int mt = PAIR ? t.m_tile(p) * 2 + static_cast<int>(rank) : t.m_tile(p);
+          const long long mrow = static_cast<long long>(mt) * kBlockM + r;
+          if (mrow < M && (!PAIR || mt < p.m_tiles_total)) {
+            const float2* st = reinterpret_cast<const float2*>(p.epi.ln_stats_in) + mrow * p.epi.ln_parts;
+            for (int pp = 0; pp < p.epi.ln_parts; ++pp) { const float2 v = __ldg(st + pp); s1 += v.x; s2 += v.y; }
+          }
+        }
+      }
+    };
+    ln_fetch(it, ln_s1n, ln_s2n);
+    (void)ln_s1n; (void)ln_s2n;
+    const uint32_t c1_s = ptx::smem_u32(&ctl->c1[0][0]);
+    (void)c1_s;
+    int te_slot = 0, ln_buf = 0;
     uint32_t te_ph = 0;
-    (void)te_slot; (void)te_ph;
+    (void)te_slot; (void)te_ph; (void)ln_buf;
     for (; it.valid(); it.next()) {
       const int n_tile = it.n_tile(p), m_tile = PAIR ? it.m_tile(p) * 2 + static_cast<int>(rank) : it.m_tile(p);
       const int n0 = n_tile * BN;
       {
 #pragma unroll
         for (int i = 0; i < kBiasPer; ++i)
-          if (bias_t + i * 32 * EW < BN) ptx::sts32(bias_s + (as * 256 + bias_t + i * 32 * EW) * 4, __float_as_uint(bias_cur[i]));
+          if (bias_t + i * 32 * EW < BN) {
+            ptx::sts32(bias_s + (as * 256 + bias_t + i * 32 * EW) * 4, __float_as_uint(bias_cur[i]));
+            if constexpr (kLNA) ptx::sts32(c1_s + (as * 256 + bias_t + i * 32 * EW) * 4, __float_as_uint(c1_cur[i]));
+          }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");  // epilogue warps only
         TileIter nx = it;
         nx.next();
-        bias_fetch(nx, bias_cur);
+        bias_fetch(nx, bias_cur, c1_cur);
+      }
+      uint64_t ln_a = 0ull, ln_b = 0ull;   // LayerNorm consumer: (rstd, rstd) and (-rstd * mean, -rstd * mean) of this thread's row
+      (void)ln_a; (void)ln_b;
+      if constexpr (kLNA) {
+        // this tile's sums were requested one tile ago (ln_s1n / ln_s2n): their latency hides behind the previous tile
+        const float inv_d = 1.f / static_cast<float>(p.epi.ln_dim);
+        const float mu = ln_s1n * inv_d;
+        const float rstd = rsqrtf(fmaxf(ln_s2n * inv_d - mu * mu, 0.f) + p.epi.ln_eps);
+        ln_a = pk2(rstd, rstd);
+        ln_b = pk2(-rstd * mu, -rstd * mu);
+        TileIter nx2 = it;
+        nx2.next();
+        ln_fetch(nx2, ln_s1n, ln_s2n);
       }
       if constexpr (TE) {
         // out = residual + (acc + bias), chunk by chunk: this thread's row of the chunk sits at r*128 in the slot,
@@ -498,12 +547,17 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
         const uint32_t bias_row = bias_s + as * 1024;
         const uint32_t ring_s = ptx::smem_u32(res_ring);
+        uint64_t ln_s1 = 0ull, ln_s2 = 0ull;   // packed (even, odd column) partial sums of x and x^2 over this tile's columns
+        (void)ln_s1; (void)ln_s2;
+        const long long ln_mrow = static_cast<long long>(m_tile) * kBlockM + r;
+        const bool ln_row_ok = LN && ln_mrow < M && (!PAIR || m_tile < m_tiles_total);
+        (void)ln_row_ok;
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t raw[32];
           ptx::tmem_ld<32>(t_row + c * 32, raw);
           ptx::mbar_wait(&ctl->res_full[te_slot], te_ph);
           ptx::tmem_ld_wait(raw);
-          const uint32_t rowaddr = ring_s + te_slot * kResSlotBytes + r * 128;
+          const uint32_t rowaddr = ring_s + te_slot * kSlot + r * 128;
           if (dbg != 2) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -516,11 +570,51 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
               upk2u(v0, o.x, o.y);
               upk2u(v1, o.z, o.w);
               ptx::sts128(a, o);
+              if constexpr (LN) {
+                ln_s1 = add2(ln_s1, add2(v0, v1));
+                ln_s2 = fma2(v0, v0, fma2(v1, v1, ln_s2));
+                raw[4 * k + 0] = o.x; raw[4 * k + 1] = o.y; raw[4 * k + 2] = o.z; raw[4 * k + 3] = o.w;   // keep x for the bf16 copy
+              }
+            }
+            if constexpr (LN) {
+              // bf16 copy of the chunk, the way the TMA-store epilogue does it: this warp's 32 rows x 64 B go into a
+              // warp-private SWIZZLE_64B tile (two alternate) and one lane hands it to a TMA store.  (Per-thread global
+              // stores of 64-byte row pieces made proj 38 % slower, a 128-row tile per ring slot cost an operand stage.)
+              if (lane == 0) ptx::bulk_wait_read<1>();   // the store issued from this tile two chunks ago has read it
+              __syncwarp();
+              const uint32_t tile_s = ptx::smem_u32(ln_copy) + ((warp - kEpiWarp0) * 2 + ln_buf) * 2048;
+              const uint32_t brow = tile_s + lane * 64;
+              const int sw = (lane >> 1) & 3;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16(__uint_as_float(raw[8 * j + 0]), __uint_as_float(raw[8 * j + 1]));
+                o.y = pack_bf16(__uint_as_float(raw[8 * j + 2]), __uint_as_float(raw[8 * j + 3]));
+                o.z = pack_bf16(__uint_as_float(raw[8 * j + 4]), __uint_as_float(raw[8 * j + 5]));
+                o.w = pack_bf16(__uint_as_float(raw[8 * j + 6]), __uint_as_float(raw[8 * j + 7]));
+                ptx::sts128(brow + ((j ^ sw) << 4), o);
+              }
+              ptx::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                if (dbg == 0) ptx::tma_store_2d_s(&p.tmCb, tile_s, n0 + c * 32, m_tile * kBlockM + q * 32);   // rows past M are clipped
+                ptx::bulk_commit();
+              }
+              ln_buf ^= 1;
             }
           }
           ptx::fence_proxy_async();
           ptx::mbar_arrive(&ctl->chunk_done[te_slot]);
           if (++te_slot == kResSlots) { te_slot = 0; te_ph ^= 1; }
+        }
+        if constexpr (LN) {
+          // this row's partial (sum x, sum x^2) over the tile's BN columns: slot n_tile of the row's ln_parts partials
+          if (ln_row_ok) {
+            float a0, a1, b0, b1;
+            upk2(ln_s1, a0, a1);
+            upk2(ln_s2, b0, b1);
+            reinterpret_cast<float2*>(p.epi.ln_stats_out)[ln_mrow * p.num_n_tiles + n_tile] = make_float2(a0 + a1, b0 + b1);
+          }
         }
         dbg_e_busy += dbg_clock(dbgt) - dbg_t_busy0;
       } else if constexpr (OUT == OUT_CLS_TAIL) {
@@ -607,6 +701,8 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
         const uint32_t bias_row = bias_s + as * 1024;
+        const uint32_t c1_row = c1_s + as * 1024;
+        (void)c1_row;
         if (dbg != 2) {
           // One 64-byte output segment (kSegCols accumulator columns) per step.  Two register sets
           // alternate so the TMEM load of the next segment is in flight while this one is processed.
@@ -634,8 +730,14 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const uint4 b = ptx::lds128(bias_row + ((c0 + sc) * 16 + 4 * i) * 4);
-                v2[2 * i] = add2(pk2u(raw[sc * 16 + 4 * i + 0], raw[sc * 16 + 4 * i + 1]), pk2u(b.x, b.y));
-                v2[2 * i + 1] = add2(pk2u(raw[sc * 16 + 4 * i + 2], raw[sc * 16 + 4 * i + 3]), pk2u(b.z, b.w));
+                if constexpr (kLNA) {   // rstd * acc - rstd * mean * c1 + c0
+                  const uint4 cc = ptx::lds128(c1_row + ((c0 + sc) * 16 + 4 * i) * 4);
+                  v2[2 * i] = fma2(pk2u(raw[sc * 16 + 4 * i + 0], raw[sc * 16 + 4 * i + 1]), ln_a, fma2(ln_b, pk2u(cc.x, cc.y), pk2u(b.x, b.y)));
+                  v2[2 * i + 1] = fma2(pk2u(raw[sc * 16 + 4 * i + 2], raw[sc * 16 + 4 * i + 3]), ln_a, fma2(ln_b, pk2u(cc.z, cc.w), pk2u(b.z, b.w)));
+                } else {
+                  v2[2 * i] = add2(pk2u(raw[sc * 16 + 4 * i + 0], raw[sc * 16 + 4 * i + 1]), pk2u(b.x, b.y));
+                  v2[2 * i + 1] = add2(pk2u(raw[sc * 16 + 4 * i + 2], raw[sc * 16 + 4 * i + 3]), pk2u(b.z, b.w));
+                }
               }
               if constexpr (RES) {
 #pragma unroll
@@ -727,7 +829,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
       ++dbg_tiles;
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if constexpr (TS) { if (lane == 0) ptx::bulk_wait<0>(); }
+    if constexpr (TS || (TE && LN)) { if (lane == 0) ptx::bulk_wait<0>(); }
     if ((p.debug & 4) && blockIdx.x == 0 && lane == 0 && (warp == kEpiWarp0 || warp == kEpiWarp0 + 4)) {
       const int o = (warp == kEpiWarp0 + 4) * 3;
       p.dbg_out[5 + o] = dbg_e_wait; p.dbg_out[6 + o] = dbg_e_busy; p.dbg_out[7 + o] = dbg_tiles;
@@ -819,7 +921,7 @@ int env_int(const char* name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
-Plan plan_tiles(int N, int Ktot, int BK, long long m_tiles, bool allow_resident, int want_pair) {
+Plan plan_tiles(int N, int Ktot, int BK, long long m_tiles, bool allow_resident, int want_pair, int min_bn = 0, int bn_mult = 1) {
   static const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
   static const int pair_env = env_int("TT_GEMM_PAIR", 1);  // 0 never, 1 cost model, 2 whenever legal (development)
   const double kL2 = 40.0, kSmem = 128.0;
@@ -833,7 +935,7 @@ Plan plan_tiles(int N, int Ktot, int BK, long long m_tiles, bool allow_resident,
     const int slots = pair ? sms / 2 : sms;
     const int res_max = pair ? kResidentMaxPair : kResidentMax;
     for (int c : cand) {
-      if (N % c != 0) continue;
+      if (N % c != 0 || c < min_bn || c % bn_mult != 0) continue;
       const int b_rows = pair ? c / 2 : c;
       const double mma = 128.0 * c * BK / 4096.0;
       const double a_bytes = 128.0 * BK * 2, b_bytes = static_cast<double>(b_rows) * BK * 2;
@@ -898,6 +1000,12 @@ int epi_warps(const Epilogue& e, int BN) {
 
 template <bool PAIR>
 void (*select_kernel_ts(const Epilogue& e, int ew))(const KParams) {
+  if (e.ln_stats_in != nullptr) {   // LayerNorm consumer: plain or GELU bf16 outputs
+    if (ew == 8) return e.act == ACT_GELU ? gemm_tc_kernel<OUT_BF16, ACT_GELU, false, PAIR, 8, false, true, true>
+                                          : gemm_tc_kernel<OUT_BF16, ACT_NONE, false, PAIR, 8, false, true, true>;
+    return e.act == ACT_GELU ? gemm_tc_kernel<OUT_BF16, ACT_GELU, false, PAIR, 16, false, true, true>
+                             : gemm_tc_kernel<OUT_BF16, ACT_NONE, false, PAIR, 16, false, true, true>;
+  }
   if (ew == 8) {
     if (e.act == ACT_RELU) return gemm_tc_kernel<OUT_BF16, ACT_RELU, false, PAIR, 8, false, true>;
     if (e.act == ACT_GELU) return gemm_tc_kernel<OUT_BF16, ACT_GELU, false, PAIR, 8, false, true>;
@@ -947,8 +1055,9 @@ bool tma_epilogue_ok(const KParams& kp) {
   const Epilogue& e = kp.epi;
   // Only for launches that fill the GPU: small ones are latency bound and gain nothing from the extra two warps and the
   // 64 KB ring (TT_GEMM_TE=2 forces it everywhere: the regime of the round-1 hang, kept for the regression probe).
-  if (te_env != 2 && kp.m_tiles_total < 2 * num_sms()) return false;
-  return te_env != 0 && kp.mode == 0 && e.out_type == OUT_F32 && e.res_type == RES_F32 && e.act == ACT_NONE && kp.BN % 32 == 0 &&
+  const bool want_stats = e.ln_stats_out != nullptr;   // the LayerNorm-statistics producer exists only as a TMA epilogue
+  if (te_env != 2 && !want_stats && kp.m_tiles_total < 2 * num_sms()) return false;
+  return (te_env != 0 || want_stats) && kp.mode == 0 && e.out_type == OUT_F32 && e.res_type == RES_F32 && e.act == ACT_NONE && kp.BN % 32 == 0 &&
          kp.N % 4 == 0 && e.ldc % 4 == 0 && e.ldr % 4 == 0 && (e.res_mod == 0 || e.res_mod % kBlockM == 0) &&
          reinterpret_cast<uintptr_t>(e.out) % 16 == 0 && reinterpret_cast<uintptr_t>(e.residual) % 16 == 0;
 }
@@ -973,11 +1082,30 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
                   reinterpret_cast<uintptr_t>(kp.epi.out) % 16 == 0;
   const int ew = te ? 4 : epi_warps(kp.epi, kp.BN);
   KernelFn fn;
+  const bool ln_prod = kp.epi.ln_stats_out != nullptr, ln_cons = kp.epi.ln_stats_in != nullptr;
+  if (ln_prod && (!te || kp.epi.ln_xb_out == nullptr || kp.epi.ldxb % 8 != 0 || reinterpret_cast<uintptr_t>(kp.epi.ln_xb_out) % 16 != 0 || kp.num_n_tiles > 4)) {
+    set_error("gemm: LayerNorm statistics need the TMA epilogue (fp32 out + fp32 residual), a bf16 copy target and <= 4 N tiles");
+    return cudaErrorInvalidValue;
+  }
+  if (ln_cons && (!ts || kp.epi.ln_c1 == nullptr || kp.epi.ln_parts <= 0 || kp.epi.ln_dim <= 0)) {
+    set_error("gemm: the LayerNorm consumer needs the TMA-store bf16 epilogue, c1 and the producer's statistics");
+    return cudaErrorInvalidValue;
+  }
   if (te) {
-    fn = kp.pair ? gemm_tc_kernel<OUT_F32, ACT_NONE, true, true, 4, true> : gemm_tc_kernel<OUT_F32, ACT_NONE, true, false, 4, true>;
+    if (ln_prod)
+      fn = kp.pair ? gemm_tc_kernel<OUT_F32, ACT_NONE, true, true, 4, true, false, true> : gemm_tc_kernel<OUT_F32, ACT_NONE, true, false, 4, true, false, true>;
+    else
+      fn = kp.pair ? gemm_tc_kernel<OUT_F32, ACT_NONE, true, true, 4, true> : gemm_tc_kernel<OUT_F32, ACT_NONE, true, false, 4, true>;
     const long long res_rows = kp.epi.res_mod > 0 ? kp.epi.res_mod : kp.M;
     if (!make_tmap_f32_chunk(&kp.tmR, kp.epi.residual, res_rows, kp.N, kp.epi.ldr)) return cudaErrorInvalidValue;
     if (!make_tmap_f32_chunk(&kp.tmC, kp.epi.out, kp.M, kp.N, kp.epi.ldc)) return cudaErrorInvalidValue;
+    if (ln_prod) {
+      const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kp.N), static_cast<cuuint64_t>(kp.M)};
+      const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kp.epi.ldxb) * 2};
+      const cuuint32_t box[2] = {32, 32};
+      if (!make_tmap_bf16(&kp.tmCb, kp.epi.ln_xb_out, 2, dims, strides, box, 64)) return cudaErrorInvalidValue;
+      if (kp.epi.ln_parts_out) *kp.epi.ln_parts_out = kp.num_n_tiles;
+    }
   } else if (ts) {
     fn = kp.pair ? select_kernel_ts<true>(kp.epi, ew) : select_kernel_ts<false>(kp.epi, ew);
     if (kp.mode == 1) {
@@ -998,7 +1126,7 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   }
   TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
   const int threads = 64 + 32 * ew + (te ? 64 : 0);
-  const int staging = te ? kResSlots * kResSlotBytes : ts ? ew * (ew == 16 ? 1 : 2) * 2048 : ew * 2048;
+  const int staging = te ? kResSlots * kResSlotBytes + (ln_prod ? kLnCopyBytes : 0) : ts ? ew * (ew == 16 ? 1 : 2) * 2048 : ew * 2048;
   const int slots = kp.pair ? max_pairs(reinterpret_cast<const void*>(fn), 200 * 1024, threads) : num_sms();
   if (kp.b_resident && (num_kb * b_bytes > (kp.pair ? kResidentMaxPair : kp.halo ? kHaloResidentMax : kResidentMax) || kp.num_n_tiles > slots)) kp.b_resident = 0;
   const int res_bytes = kp.b_resident ? num_kb * b_bytes : 0;
@@ -1178,7 +1306,15 @@ cudaError_t linear_forward(const LinearProblem& l, const Epilogue& e, cudaStream
   kp.M = l.M; kp.N = l.N;
   kp.num_m_tiles = (l.M + kBlockM - 1) / kBlockM;
   {
-    const Plan pl = plan_tiles(l.N, l.K, kp.BK, kp.num_m_tiles, l.resident != 0, l.pair);
+    // LayerNorm producer: at most 4 N tiles (statistics slots); both LayerNorm roles need whole 32-column TMA boxes
+    const bool ln_any = e.ln_stats_out != nullptr || e.ln_stats_in != nullptr;
+    // The producer's N tile is a function of N alone (the widest legal one): the partial sums' grouping, and with it every
+    // bit downstream, must not depend on the batch size (test_parseq_full_batch_is_batch_invariant).
+    int ln_bn = 0;
+    if (e.ln_stats_out)
+      for (int c : {256, 192, 128, 96, 64, 32})
+        if (l.N % c == 0 && l.N / c <= 4) { ln_bn = c; break; }
+    const Plan pl = plan_tiles(l.N, l.K, kp.BK, kp.num_m_tiles, l.resident != 0, l.pair, ln_bn, ln_any ? 32 : 1);
     kp.BN = l.BN ? l.BN : pl.BN;
     kp.b_resident = l.BN ? (l.resident == 1) : pl.resident;
     kp.pair = l.BN ? (l.pair == 1) : pl.pair;

@@ -28,6 +28,20 @@ struct Epilogue {
   // OUT_CLS_TAIL: after bias+ReLU on the 16 accumulators, two 1x1 convs in registers
   // (16->16 ReLU, 16->2) and an fp32 [pixel][2] store.  tail = {w4[16][16], b4[16], w5[2][16], b5[2]}
   const float* tail = nullptr;
+  // ---- LayerNorm fused away (PARSeq encoder: x -> LN -> Linear).  With W' = W * gamma (folded at export),
+  //   Linear(LN(x))[n] = rstd * (x . W'[n]) - rstd * mean * c1[n] + c0[n],  c1[n] = sum_k W'[n][k], c0[n] = b[n] + beta . W[n]
+  // so the GEMM reads the UN-normalised row as bf16 and its epilogue applies the row's (mean, rstd).
+  // Producer (fp32 out + residual, TMA epilogue): also emit bf16(x) and, per row and N tile, (sum x, sum x^2).
+  __nv_bfloat16* ln_xb_out = nullptr;  // [M][ldxb] bf16 copy of the output rows
+  int ldxb = 0;
+  float* ln_stats_out = nullptr;       // [M][ln_parts][2] fp32 partial sums; ln_parts = N / BN is written to *ln_parts_out
+  int* ln_parts_out = nullptr;
+  // Consumer (bf16 out): `bias` holds c0, ln_c1 holds c1, ln_stats_in the producer's partial sums over ln_dim columns.
+  const float* ln_stats_in = nullptr;
+  const float* ln_c1 = nullptr;
+  int ln_parts = 0;
+  int ln_dim = 0;
+  float ln_eps = 1e-6f;
 };
 
 struct ConvSrc {

@@ -223,7 +223,7 @@ cudaError_t DeviceCtx::craft_forward(const uint8_t* in, int B, int H, int W, flo
 size_t DeviceCtx::parseq_bytes(int n) const {
   const ParseqDims& pd = w->pd;
   const size_t M = static_cast<size_t>(n) * 128, D = pd.D;
-  size_t b = M * D * 4 + M * D * 2 + M * 3 * D * 2 + M * D * 2 + M * pd.mlp * 2 + M * D * 2 + M * 2 * D * 2;  // encoder
+  size_t b = M * D * 4 + M * D * 2 + M * 3 * D * 2 + M * D * 2 + M * pd.mlp * 2 + M * D * 2 + M * 32 + M * 2 * D * 2;  // encoder
   const size_t R = static_cast<size_t>(n) * pd.L;
   b += R * 4 + R * D * (4 + 2 + 2 + 2) + R * pd.mlp * 2 + 2 * R * pd.n_cls_pad * 4 + 2 * R * 4;
   b += dec_dense_scratch_floats(n, pd.D) * 4;
@@ -258,13 +258,42 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
   static const int chunk_env = std::getenv("TT_ENC_CHUNK") ? std::atoi(std::getenv("TT_ENC_CHUNK")) : 0;
   const int chunk = chunk_env > 0 ? std::min(chunk_env, n) : n;
   const size_t Mc = static_cast<size_t>(chunk) * 128;
+  // LayerNorm fused away (gemm_tc.cuh, Epilogue::ln_*): the residual GEMMs (patch embedding, proj, fc2) also emit
+  // bf16(x) and the rows' (sum, sum of squares); qkv / fc1 / the memory K|V projection read bf16(x) with gamma folded
+  // into their weights and apply (mean, rstd) in the epilogue.  Needs the folded tensors of the current weights.py;
+  // TT_ENC_LNFUSE=0 keeps the standalone LayerNorm kernel (A/B runs, parity test).
+  const char* lnf_env = std::getenv("TT_ENC_LNFUSE");
+  const bool lnf = !(lnf_env && std::atoi(lnf_env) == 0) && wf.has("b0.qkv.wf") && wf.has("dec.ca.kvf.wf");
   ARENA_GET(x, float, Mc * D);       // fp32 residual stream
-  ARENA_GET(h, bf, Mc * D);          // LayerNorm output / attention output
+  ARENA_GET(h, bf, Mc * D);          // LayerNorm output (unfused) / bf16 copy of x (fused)
   ARENA_GET(qkv, bf, Mc * 3 * D);
   ARENA_GET(att, bf, Mc * D);
   ARENA_GET(hid, bf, Mc * pd.mlp);
   ARENA_GET(mem, bf, Mc * D);
+  ARENA_GET(lnstats, float, Mc * 8);  // fused: per row up to 4 partial (sum, sum of squares)
   ARENA_GET(mem_kv, bf, static_cast<size_t>(M) * 2 * D);
+
+  // residual GEMM x (+)= A W^T + b [+ table]; fused mode: also bf16(x) -> h and the LayerNorm partial sums
+  int ln_parts = 0;
+  auto res_gemm = [&](const bf* A, int lda, int Mi, int K, const bf* W, const float* bias, const float* res, int res_mod) -> cudaError_t {
+    LinearProblem l;
+    l.A = A; l.lda = lda; l.M = Mi; l.K = K; l.W = W; l.N = D;
+    Epilogue e;
+    e.bias = bias; e.residual = res; e.res_type = RES_F32; e.ldr = D; e.res_mod = res_mod;
+    e.out = x; e.out_type = OUT_F32; e.ldc = D;
+    if (lnf) { e.ln_xb_out = h; e.ldxb = D; e.ln_stats_out = lnstats; e.ln_parts_out = &ln_parts; }
+    return linear_forward(l, e, s);
+  };
+  // y = Linear(LN(x)) [GELU]: fused mode reads h = bf16(x) with the folded weights `name`.wf / .c0 / .c1
+  auto ln_gemm = [&](const std::string& name, int Mi, int N, int act, bf* out) -> cudaError_t {
+    LinearProblem l;
+    l.A = h; l.lda = D; l.M = Mi; l.K = D; l.W = wf.bf(name + (lnf ? ".wf" : ".w")); l.N = N;
+    Epilogue e;
+    e.bias = wf.f32(name + (lnf ? ".c0" : ".b")); e.act = act;
+    e.out = out; e.out_type = OUT_BF16; e.ldc = N;
+    if (lnf) { e.ln_stats_in = lnstats; e.ln_c1 = wf.f32(name + ".c1"); e.ln_parts = ln_parts; e.ln_dim = D; e.ln_eps = 1e-6f; }
+    return linear_forward(l, e, s);
+  };
 
   stage_begin(s);
   for (int c0 = 0; c0 < n; c0 += chunk) {
@@ -272,21 +301,26 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
     const int Mi = nc * 128;
     const bf* pch = patches + static_cast<size_t>(c0) * 128 * 96;
     // patch embedding (Conv2d k=s=(4,8) as a K=96 GEMM) + bias + pos_embed
-    RUN(lin(s, pch, 96, Mi, 96, wf.bf("pe.w"), D, wf.f32("pe.b"), ACT_NONE, wf.f32("pos"), RES_F32, D, 128, x, OUT_F32, D));
+    RUN(res_gemm(pch, 96, Mi, 96, wf.bf("pe.w"), wf.f32("pe.b"), wf.f32("pos"), 128));
     for (int i = 0; i < pd.depth; ++i) {
       const std::string p = "b" + std::to_string(i) + ".";
-      RUN(layernorm(x, Mi, D, wf.f32(p + "ln1.g"), wf.f32(p + "ln1.b"), 1e-6f, h, nullptr, 0, s));
-      RUN(lin(s, h, D, Mi, D, wf.bf(p + "qkv.w"), 3 * D, wf.f32(p + "qkv.b"), ACT_NONE, nullptr, RES_NONE, 0, 0, qkv, OUT_BF16, 3 * D));
+      if (!lnf) RUN(layernorm(x, Mi, D, wf.f32(p + "ln1.g"), wf.f32(p + "ln1.b"), 1e-6f, h, nullptr, 0, s));
+      RUN(ln_gemm(p + "qkv", Mi, 3 * D, ACT_NONE, qkv));
       RUN(attention_enc(qkv, att, nc, D, pd.enc_heads, s));
-      RUN(lin(s, att, D, Mi, D, wf.bf(p + "proj.w"), D, wf.f32(p + "proj.b"), ACT_NONE, x, RES_F32, D, 0, x, OUT_F32, D));
-      RUN(layernorm(x, Mi, D, wf.f32(p + "ln2.g"), wf.f32(p + "ln2.b"), 1e-6f, h, nullptr, 0, s));
-      RUN(lin(s, h, D, Mi, D, wf.bf(p + "fc1.w"), pd.mlp, wf.f32(p + "fc1.b"), ACT_GELU, nullptr, RES_NONE, 0, 0, hid, OUT_BF16, pd.mlp));
-      RUN(lin(s, hid, pd.mlp, Mi, pd.mlp, wf.bf(p + "fc2.w"), D, wf.f32(p + "fc2.b"), ACT_NONE, x, RES_F32, D, 0, x, OUT_F32, D));
+      RUN(res_gemm(att, D, Mi, D, wf.bf(p + "proj.w"), wf.f32(p + "proj.b"), x, 0));
+      if (!lnf) RUN(layernorm(x, Mi, D, wf.f32(p + "ln2.g"), wf.f32(p + "ln2.b"), 1e-6f, h, nullptr, 0, s));
+      RUN(ln_gemm(p + "fc1", Mi, pd.mlp, ACT_GELU, hid));
+      RUN(res_gemm(hid, pd.mlp, Mi, pd.mlp, wf.bf(p + "fc2.w"), wf.f32(p + "fc2.b"), x, 0));
     }
-    RUN(layernorm(x, Mi, D, wf.f32("enc.ln.g"), wf.f32("enc.ln.b"), 1e-6f, mem, nullptr, 0, s));
-    // cross-attention K/V of the memory, once per crop (rows D.. of cross_attn.in_proj)
-    RUN(lin(s, mem, D, Mi, D, wf.bf("dec.ca.in.w") + static_cast<size_t>(D) * D, 2 * D, wf.f32("dec.ca.in.b") + D, ACT_NONE,
-            nullptr, RES_NONE, 0, 0, mem_kv + static_cast<size_t>(c0) * 128 * 2 * D, OUT_BF16, 2 * D));
+    // cross-attention K/V of the memory = rows D.. of cross_attn.in_proj applied to the encoder's final LayerNorm, once per crop
+    bf* mkv = mem_kv + static_cast<size_t>(c0) * 128 * 2 * D;
+    if (lnf) {
+      RUN(ln_gemm("dec.ca.kvf", Mi, 2 * D, ACT_NONE, mkv));
+    } else {
+      RUN(layernorm(x, Mi, D, wf.f32("enc.ln.g"), wf.f32("enc.ln.b"), 1e-6f, mem, nullptr, 0, s));
+      RUN(lin(s, mem, D, Mi, D, wf.bf("dec.ca.in.w") + static_cast<size_t>(D) * D, 2 * D, wf.f32("dec.ca.in.b") + D, ACT_NONE,
+              nullptr, RES_NONE, 0, 0, mkv, OUT_BF16, 2 * D));
+    }
   }
 
   stage_end(s, "parseq_encoder", 5.75e9 * n, 0.0);  // 2 x 2.874 GMAC per crop

@@ -142,6 +142,22 @@ def export_parseq(state_dict: dict, path: str | Path) -> None:
         out[f"b{i}.fc1.w"], out[f"b{i}.fc1.b"] = bf(sd[p + "mlp.fc1.weight"]), sd[p + "mlp.fc1.bias"]
         out[f"b{i}.fc2.w"], out[f"b{i}.fc2.b"] = bf(sd[p + "mlp.fc2.weight"]), sd[p + "mlp.fc2.bias"]
     out["enc.ln.g"], out["enc.ln.b"] = sd["encoder.norm.weight"], sd["encoder.norm.bias"]
+
+    # LayerNorm folded into the Linear that follows it (gemm_tc.cuh, Epilogue::ln_*):
+    #   Linear(LN(x))[n] = rstd * (x . W'[n]) - rstd * mean * c1[n] + c0[n],   W' = W * gamma (bf16),
+    #   c1[n] = sum_k W'[n][k] (of the ROUNDED values, so the mean term cancels exactly), c0[n] = b[n] + beta . W[n]
+    def fold_ln(name, w, b, g, beta):
+        wf_ = (w * g[None, :]).to(torch.bfloat16)
+        out[name + ".wf"] = wf_.contiguous()
+        out[name + ".c1"] = wf_.double().sum(1).float()
+        out[name + ".c0"] = (b.double() + w.double() @ beta.double()).float()
+
+    for i in range(depth):
+        p = f"encoder.blocks.{i}."
+        fold_ln(f"b{i}.qkv", sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"], sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+        fold_ln(f"b{i}.fc1", sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"], sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+    ca_w, ca_b = sd["decoder.layers.0.cross_attn.in_proj_weight"], sd["decoder.layers.0.cross_attn.in_proj_bias"]
+    fold_ln("dec.ca.kvf", ca_w[d:], ca_b[d:], sd["encoder.norm.weight"], sd["encoder.norm.bias"])
     L = "decoder.layers.0."
     for short, full in (("nq", "norm_q"), ("nc", "norm_c"), ("n1", "norm1"), ("n2", "norm2")):
         out[f"dec.{short}.g"], out[f"dec.{short}.b"] = sd[L + full + ".weight"], sd[L + full + ".bias"]
