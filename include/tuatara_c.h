@@ -142,6 +142,11 @@ TT_API int tt_postprocess(const float* maps, int H, int W, const tt_config* cfg,
 /* Crop + resize to 128x32 (tuatara.cpp:416, :440-441). rects_xywh already clamped to the image.
  * out: [n][32][128][3] u8 in the caller's channel order. */
 TT_API int tt_crop_resize(const tt_image* image, const int32_t* rects_xywh, int n, uint8_t* out);
+/* Per-slice parity of the CRAFT forward: a named activation of the LAST tt_craft_forward call on this
+ * engine as fp32 [H][W][C] (names: relu2_2, relu3_2, relu4_3, relu5_3, fc7, up1, up2, up3, up4 -- upstream CRAFT's
+ * skip / U-net tensors).  out == NULL only reports dims_out = {H, W, C}.  Test entry point: not thread safe against
+ * other calls on the same engine. */
+TT_API int tt_craft_tap(tt_engine* e, const char* name, float* out, long long capacity, int dims_out[3]);
 /* PARSeq forward (tuatara.cpp:307, 26 AR steps + 1 refinement). crops: [n][32][128][3] u8.
  * forced_tokens (nullable) [n][25]: teacher-forced AR context (parity tests).
  * logits_out (nullable) [n][26][95] fp32; ids_out (nullable) [n][26] argmax (== softmax + max, :486,:103). */

@@ -153,3 +153,31 @@ def test_mixed_page_sizes_share_one_recognition_batch(engine):
     for i in range(len(shapes)):
         alone = engine.ocr_pages([pages[i]], score_override=[maps[i]])[0]
         assert alone == together[i], i
+
+
+def test_pytuatara_module_against_the_oracle(engine, weights_dir, oracle_models, native_lib):
+    """The reference's Python module (bindings/python.cpp:54-58) with real weight files on the GPU.  The module has no
+    score-map override, and random-init CRAFT maps are near constant (min-max normalisation then amplifies bf16 noise),
+    so the oracle is fed the raw maps the CUDA CRAFT produced for the same page: from there on (normalise, CCL, boxes,
+    crops, PARSeq, decode, formatting) pytuatara's result must equal the oracle's."""
+    import sys
+
+    from tuatara_b200 import _native
+    sys.path.insert(0, str(_native.LIB_PATH.parent))
+    import pytuatara
+
+    craft, parseq = oracle_models
+    n_boxes = 0
+    for seed, (h, w) in ((0, (607, 763)), (1, (512, 640)), (2, (754, 1000))):
+        page = np.ascontiguousarray(synth.synth_page(seed)[:h, :w])
+        got = pytuatara.image_to_data(image=page.copy(), weights_dir=weights_dir, outputs_dir="outputs")
+        assert isinstance(got, list) and all(set(g) == {"text", "bbox"} and len(g["bbox"]) == 4 for g in got)
+        craft_in, _ = tb.preprocess(page)
+        maps = engine.craft_forward(craft_in)
+        ref = R.image_to_data(page.copy(), craft, parseq, score_override=(maps[..., 0], maps[..., 1]))
+        assert [g["bbox"] for g in got] == [r["bbox"] for r in ref], (seed, len(got), len(ref))
+        same = sum(g["text"] == r["text"] for g, r in zip(got, ref))
+        assert same >= 0.8 * len(ref), f"page {seed}: {same}/{len(ref)} strings equal"
+        assert got == tb.image_to_data(page, weights_dir, "outputs")   # the ctypes twin takes the same path
+        n_boxes += len(got)
+    assert n_boxes > 0

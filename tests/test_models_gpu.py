@@ -41,6 +41,30 @@ def test_craft_score_maps(engine, oracle_models, kind):
     assert err <= 3e-2, f"raw score maps rel-L2 {err:.4f}"
 
 
+def test_craft_per_slice_parity(engine, oracle_models):
+    """every CRAFT slice against the fp32 oracle, so a regression names its layer.  Bars (bf16 operands,
+    fp32 accumulate, BN folded): rel-L2 <= 1e-2 on the VGG slices and fc7, <= 2e-2 on the U-net stages (each stacks
+    two more convolutions and a bilinear upsample on the slices), final maps <= 3e-2 (test_craft_score_maps)."""
+    craft, _ = oracle_models
+    craft_in, _ = tb.preprocess(synth.synth_page(3)[:640, :768])
+    x = torch.from_numpy(craft_in)[None].permute(0, 3, 1, 2).float().div(255.0)
+    taps = {}
+    with torch.no_grad():
+        craft(x, taps=taps)
+    engine.craft_forward(craft_in)
+    bars = {"relu2_2": 1e-2, "relu3_2": 1e-2, "relu4_3": 1e-2, "relu5_3": 1e-2, "fc7": 1e-2,
+            "up1": 2e-2, "up2": 2e-2, "up3": 2e-2, "up4": 2e-2}
+    worst = {}
+    for name, bar in bars.items():
+        ref = taps[name][0].permute(1, 2, 0).numpy()
+        got = engine.craft_tap(name)
+        assert got.shape == ref.shape, (name, got.shape, ref.shape)
+        worst[name] = _rel_l2(got, ref)
+    print("CRAFT per-slice rel-L2:", {k: round(v, 5) for k, v in worst.items()})
+    for name, bar in bars.items():
+        assert worst[name] <= bar, f"{name}: rel-L2 {worst[name]:.4f} > {bar}"
+
+
 def _crops(n, seed=0):
     img = synth.synth_page(seed)
     rng = np.random.default_rng(seed)

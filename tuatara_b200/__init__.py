@@ -225,6 +225,14 @@ class Engine:
         check(lib().tt_craft_forward(self._h, ptr(x), h32, w32, ptr(out)), "tt_craft_forward")
         return out
 
+    def craft_tap(self, name: str) -> np.ndarray:
+        """A named activation of the last craft_forward() as float32 [H, W, C] (per-slice parity tests)."""
+        dims = (C.c_int * 3)()
+        check(lib().tt_craft_tap(self._h, name.encode(), None, 0, dims), "tt_craft_tap")
+        out = np.empty((dims[0], dims[1], dims[2]), np.float32)
+        check(lib().tt_craft_tap(self._h, name.encode(), ptr(out), out.size, dims), "tt_craft_tap")
+        return out
+
     def parseq_forward(self, crops_u8: np.ndarray, forced_tokens: np.ndarray | None = None):
         """crops_u8: uint8 [n, 32, 128, 3] -> (logits float32 [n, 26, 95], ids int32 [n, 26])."""
         x = np.ascontiguousarray(crops_u8, np.uint8)

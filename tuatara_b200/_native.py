@@ -75,6 +75,7 @@ SIGNATURES = {
     "tt_craft_forward": (_I, [_P, _P, _I, _I, _P]),
     "tt_postprocess": (_I, [_P, _I, _I, C.POINTER(tt_config), _P, _P, _I, _PI, _P, _P, _I, _PI]),
     "tt_crop_resize": (_I, [C.POINTER(tt_image), _P, _I, _P]),
+    "tt_craft_tap": (_I, [_P, C.c_char_p, _P, C.c_longlong, _P]),
     "tt_parseq_forward": (_I, [_P, _P, _I, _P, _P, _P]),
     "tt_decode": (_I, [_P, _I, _I, _P, _I]),
     "tt_tokenizer_table": (_I, [C.c_char_p, _PI, _PI, _PI]),

@@ -494,6 +494,31 @@ int tt_craft_forward(tt_engine* e, const uint8_t* craft_input, int h32, int w32,
   }
 }
 
+int tt_craft_tap(tt_engine* e, const char* name, float* out, long long capacity, int dims_out[3]) {
+  try {
+    if (!e || !name) { set_error("tt_craft_tap: null argument"); return 1; }
+    DeviceCtx& d = *e->devs[0];
+    std::lock_guard<std::mutex> lock(d.mu);
+    E_CUDA(cudaSetDevice(d.device));
+    for (const CraftTap& t : d.craft_taps) {
+      if (std::strcmp(t.name, name) != 0) continue;
+      const long long n = static_cast<long long>(t.H) * t.W * t.C;
+      if (dims_out) { dims_out[0] = t.H; dims_out[1] = t.W; dims_out[2] = t.C; }
+      if (!out) return 0;
+      if (capacity < n) { set_error("tt_craft_tap: output buffer too small"); return 1; }
+      std::vector<__nv_bfloat16> h(static_cast<size_t>(n));
+      E_CUDA(cudaMemcpy(h.data(), t.ptr, sizeof(__nv_bfloat16) * n, cudaMemcpyDeviceToHost));
+      for (long long i = 0; i < n; ++i) out[i] = __bfloat162float(h[static_cast<size_t>(i)]);
+      return 0;
+    }
+    set_error(std::string("tt_craft_tap: no activation named '") + name + "' (run tt_craft_forward first)");
+    return 1;
+  } catch (const std::exception& ex) {
+    set_error(std::string("tt_craft_tap: ") + ex.what());
+    return 1;
+  }
+}
+
 int tt_parseq_forward(tt_engine* e, const uint8_t* crops, int n, const int32_t* forced_tokens, float* logits_out,
                       int32_t* ids_out) {
   try {

@@ -81,8 +81,12 @@ struct DeviceWeights {
 // assembly, D2H waits) are covered by the other slot's kernels.
 constexpr int kSlotsPerDevice = 4;   // upper bound; tt_config.slots_per_gpu picks how many run (0 = default 2)
 
+// A named CRAFT activation of the most recent craft_forward (arena memory: valid until the slot's next call).
+struct CraftTap { const char* name; const __nv_bfloat16* ptr; int C, H, W; };
+
 struct DeviceCtx {
   int device = 0;
+  std::vector<CraftTap> craft_taps;   // per-slice parity test (tt_craft_tap): image 0 of the batch
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // second half of a recognition batch's AR loop (overlaps the first half's cross attention)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

@@ -216,6 +216,10 @@ cudaError_t DeviceCtx::craft_forward(const uint8_t* in, int B, int H, int W, flo
     RUN(conv_forward(c, e, s));
   }
   *maps_out = maps;
+  // per-slice parity (names as the oracle's taps: oracle/models.py CRAFT.forward)
+  craft_taps = {{"relu2_2", s1, 128, H2, W2}, {"relu3_2", s2, 256, H4, W4}, {"relu4_3", s3, 512, H8, W8},
+                {"relu5_3", s4, 512, H16, W16}, {"fc7", f7, 1024, H16, W16}, {"up1", y1, 256, H16, W16},
+                {"up2", y2, 128, H8, W8}, {"up3", y3, 64, H4, W4}, {"up4", y4, 32, H2, W2}};
   return cudaSuccess;
 }
 
