@@ -183,6 +183,51 @@ def test_parseq_encoder_layernorm_fusion_matches_unfused(engine, monkeypatch):
     assert (idf[clear] == idu[clear]).all()
 
 
+def test_parseq_tiny_variant(oracle_models):
+    """PARSeq-tiny (embed 192, 3 encoder / 6 decoder heads, MLP 768: the other variant the HuggingFace checkpoint may be,
+    /root/reference/.gitignore:1): dims come from the weight file's meta tensor; logits against the fp32 oracle under
+    the oracle's own AR context, ids wherever its decision is clear, both decoder paths."""
+    import os
+
+    from conftest import ROOT
+    from oracle.models import make_parseq
+    from tuatara_b200 import weights
+
+    craft, _ = oracle_models
+    tiny = make_parseq("tiny", 0)
+    d = ROOT / "tests" / "_cache" / "weights_tiny_seed0"
+    d.mkdir(parents=True, exist_ok=True)
+    if not (d / "craft.ttw").exists():
+        weights.export_craft(craft.state_dict(), d / "craft.ttw")
+    if not (d / "parseq.ttw").exists():
+        weights.export_parseq(tiny.state_dict(), d / "parseq.ttw")
+    eng = tb.Engine(str(d), devices=[0])
+    try:
+        crops = _crops(40, seed=9)
+        x = torch.from_numpy(crops).permute(0, 3, 1, 2).float().div(255.0)
+        taps = {}
+        tiny(x, taps=taps)
+        forced = taps["ar_tokens"][:, 1:].clone()
+        ref = tiny(x, forced_tokens=forced).numpy()
+        for fused in ("1", "0"):
+            os.environ["TT_DEC_FUSED"] = fused
+            try:
+                got, ids = eng.parseq_forward(crops, forced.numpy().astype(np.int32))
+            finally:
+                os.environ.pop("TT_DEC_FUSED")
+            err = _rel_l2(got, ref)
+            print("tiny logits rel-L2", err, "(fused decoder" if fused == "1" else "(unfused decoder", ")")
+            assert np.isfinite(got).all() and err <= 3e-2, err
+            top2 = np.sort(ref, -1)[..., -2:]
+            clear = (top2[..., 1] - top2[..., 0]) > 0.5
+            assert (ids[clear] == ref.argmax(-1)[clear]).all()
+        # whole path with the tiny recogniser: same boxes as with any recogniser, strings decode
+        out = eng.ocr_pages([synth.synth_page(0)], score_override=[synth.synth_score_maps(0)])[0]
+        assert len(out) == 300 and all(isinstance(o["text"], str) for o in out)
+    finally:
+        eng.close()
+
+
 def test_decode_matches_reference_tokenizer(native_lib):
     rng = np.random.default_rng(0)
     tok = R.Tokenizer()

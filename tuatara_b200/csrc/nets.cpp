@@ -469,7 +469,11 @@ cudaError_t DeviceCtx::init(const std::string& dir, std::shared_ptr<DeviceWeight
     pd.n_cls_pad = (pd.n_cls + 15) / 16 * 16;
     pd.eos_id = 0; pd.bos_id = pd.n_tok - 2; pd.pad_id = pd.n_tok - 1;
   }
-  if (pd.D != 384) { set_error("only PARSeq-base (embed_dim 384) is built in this round"); return cudaErrorInvalidValue; }
+  // PARSeq-base (384 / 6 / 12 heads) and PARSeq-tiny (192 / 3 / 6): head dims are 64 (encoder) and 32 (decoder) in both
+  if (!(pd.D == 384 || pd.D == 192) || pd.enc_heads * 64 != pd.D || pd.dec_heads * 32 != pd.D || pd.L > 32 || pd.mlp % 128 != 0) {
+    set_error("unsupported PARSeq dimensions (built for embed_dim 384 and 192, head dims 64 / 32, <= 32 positions)");
+    return cudaErrorInvalidValue;
+  }
   // self-attention queries: W_q LN_q(pos_queries) + b_q, identical for every crop
   const WeightFile& wf = w->parseq;
   const int D = pd.D, L = pd.L, NT = pd.n_tok;

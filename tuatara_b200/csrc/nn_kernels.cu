@@ -115,11 +115,15 @@ int grid_for(long long total, int block) {
 }
 
 // ------------------------------------------------------------------------------- LayerNorm
+// warp per row; a lane holds PER_LANE elements as PER_LANE / V vectors of V floats (V = 4 when PER_LANE % 4 == 0: D = 384,
+// else 2: D = 192), vector j of a lane covers columns (j * 32 + lane) * V ..
 template <int PER_LANE>
 __global__ void k_layernorm(const float* __restrict__ x, int rows, const float* __restrict__ gamma,
                             const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ ob,
                             float* __restrict__ of, int rows_mod) {
   constexpr int D = PER_LANE * 32;
+  constexpr int V = (PER_LANE % 4 == 0) ? 4 : 2;
+  static_assert(PER_LANE % V == 0, "LayerNorm width");
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -127,10 +131,17 @@ __global__ void k_layernorm(const float* __restrict__ x, int rows, const float* 
   float v[PER_LANE];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < PER_LANE / 4; ++i) {
-    const float4 t = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
-    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-    sum += t.x + t.y + t.z + t.w;
+  for (int i = 0; i < PER_LANE / V; ++i) {
+    const int col = (i * 32 + lane) * V;
+    if constexpr (V == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(xr + col);
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      sum += t.x + t.y + t.z + t.w;
+    } else {
+      const float2 t = *reinterpret_cast<const float2*>(xr + col);
+      v[2 * i] = t.x; v[2 * i + 1] = t.y;
+      sum += t.x + t.y;
+    }
   }
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float mean = sum / D;
@@ -140,20 +151,23 @@ __global__ void k_layernorm(const float* __restrict__ x, int rows, const float* 
   for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
   const float rstd = rsqrtf(var / D + eps);
 #pragma unroll
-  for (int i = 0; i < PER_LANE / 4; ++i) {
-    const int col = (i * 32 + lane) * 4;
-    const float4 g = *reinterpret_cast<const float4*>(gamma + col);
-    const float4 b = *reinterpret_cast<const float4*>(beta + col);
-    const float o0 = (v[4 * i] - mean) * rstd * g.x + b.x, o1 = (v[4 * i + 1] - mean) * rstd * g.y + b.y;
-    const float o2 = (v[4 * i + 2] - mean) * rstd * g.z + b.z, o3 = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
+  for (int i = 0; i < PER_LANE / V; ++i) {
+    const int col = (i * 32 + lane) * V;
+    float o[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) o[e] = (v[V * i + e] - mean) * rstd * gamma[col + e] + beta[col + e];
     if (ob != nullptr) {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&p0);
-      u.y = *reinterpret_cast<uint32_t*>(&p1);
-      *reinterpret_cast<uint2*>(ob + static_cast<long long>(row) * D + col) = u;
+#pragma unroll
+      for (int e = 0; e < V; e += 2) {
+        __nv_bfloat162 p = __floats2bfloat162_rn(o[e], o[e + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(ob + static_cast<long long>(row) * D + col + e) = p;
+      }
     }
-    if (of != nullptr) *reinterpret_cast<float4*>(of + static_cast<long long>(row) * D + col) = make_float4(o0, o1, o2, o3);
+    if (of != nullptr) {
+#pragma unroll
+      for (int e = 0; e < V; e += 2)
+        *reinterpret_cast<float2*>(of + static_cast<long long>(row) * D + col + e) = make_float2(o[e], o[e + 1]);
+    }
   }
 }
 
@@ -430,11 +444,12 @@ __global__ void __launch_bounds__(256) k_dec_self_attn_ar(int n, int D, int L, i
   const int tok = lane < nkeys ? tokens[crop * L + lane] : 0;
   float sc[HEADS];
   if (lane < nkeys) {
-    const float4* src = reinterpret_cast<const float4*>(sc_table + ((static_cast<long long>(step) * L + lane) * n_tok + tok) * HEADS);
+    // HEADS * 4 contiguous bytes (48 / 24): 8-byte loads keep both widths aligned
+    const float2* src = reinterpret_cast<const float2*>(sc_table + ((static_cast<long long>(step) * L + lane) * n_tok + tok) * HEADS);
 #pragma unroll
-    for (int h4 = 0; h4 < HEADS / 4; ++h4) {
-      const float4 v = __ldg(src + h4);
-      sc[4 * h4] = v.x; sc[4 * h4 + 1] = v.y; sc[4 * h4 + 2] = v.z; sc[4 * h4 + 3] = v.w;
+    for (int h2 = 0; h2 < HEADS / 2; ++h2) {
+      const float2 v = __ldg(src + h2);
+      sc[2 * h2] = v.x; sc[2 * h2 + 1] = v.y;
     }
   } else {
 #pragma unroll
@@ -498,10 +513,11 @@ __global__ void __launch_bounds__(256) k_dec_self_attn_ar(int n, int D, int L, i
 // w, w+12, ... and reads each K row as 16-byte units (unit u = head u/4, dims (u%4)*8..+8), dots it with
 // the matching slice of q, reduces over the 4 lanes of a head -> all heads' scores for that key.  After a
 // per-head softmax in smem the V rows are streamed the same way and the 12 warps' partial sums combined.
-__global__ void __launch_bounds__(384) k_dec_cross_attn(DecoderStep st, const __nv_bfloat16* __restrict__ q,
-                                                        const __nv_bfloat16* __restrict__ mem_kv,
-                                                        __nv_bfloat16* __restrict__ out) {
-  constexpr int kD = 384, kHeads = 12, kKeys = 128, kWarps = 12, kUnits = kD / 8;  // 48 16-byte units per K row
+template <int kD>
+__global__ void __launch_bounds__(kD) k_dec_cross_attn(DecoderStep st, const __nv_bfloat16* __restrict__ q,
+                                                       const __nv_bfloat16* __restrict__ mem_kv,
+                                                       __nv_bfloat16* __restrict__ out) {
+  constexpr int kHeads = kD / 32, kKeys = 128, kWarps = kHeads, kUnits = kD / 8;  // 48 (base) / 24 (tiny) 16-byte units per K row
   __shared__ float s_sc[kHeads][kKeys];         // scores, then probabilities
   __shared__ float s_part[kWarps][kD];          // per-warp partial outputs
   const int pi = blockIdx.x, crop = blockIdx.y;
@@ -510,15 +526,19 @@ __global__ void __launch_bounds__(384) k_dec_cross_attn(DecoderStep st, const __
   const __nv_bfloat16* kvb = mem_kv + static_cast<long long>(crop) * kKeys * 2 * kD;
   // q slices for the (up to) two units this lane covers: unit lane, unit 32 + lane (lane < 16)
   float qa[8], qb[8];
-  unpack8(*reinterpret_cast<const uint4*>(q + row * kD + lane * 8), qa);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { qa[i] = 0.f; qb[i] = 0.f; }
+  if (lane < kUnits) unpack8(*reinterpret_cast<const uint4*>(q + row * kD + lane * 8), qa);
   if (lane < kUnits - 32) unpack8(*reinterpret_cast<const uint4*>(q + row * kD + (32 + lane) * 8), qb);
   for (int key = warp; key < kKeys; key += kWarps) {
     const uint4* kr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(key) * 2 * kD);
     float f[8];
-    unpack8(__ldg(kr + lane), f);
     float a = 0.f, b = 0.f;
+    if (lane < kUnits) {
+      unpack8(__ldg(kr + lane), f);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a += qa[i] * f[i];
+      for (int i = 0; i < 8; ++i) a += qa[i] * f[i];
+    }
     if (lane < kUnits - 32) {
       unpack8(__ldg(kr + 32 + lane), f);
 #pragma unroll
@@ -527,7 +547,7 @@ __global__ void __launch_bounds__(384) k_dec_cross_attn(DecoderStep st, const __
     a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
     b += __shfl_xor_sync(0xffffffffu, b, 1); b += __shfl_xor_sync(0xffffffffu, b, 2);
     if ((lane & 3) == 0) {
-      s_sc[lane >> 2][key] = a * 0.17677669529663687f;
+      if (lane < kUnits) s_sc[lane >> 2][key] = a * 0.17677669529663687f;
       if (lane < kUnits - 32) s_sc[8 + (lane >> 2)][key] = b * 0.17677669529663687f;
     }
   }
@@ -552,10 +572,12 @@ __global__ void __launch_bounds__(384) k_dec_cross_attn(DecoderStep st, const __
   for (int key = warp; key < kKeys; key += kWarps) {
     const uint4* vr = reinterpret_cast<const uint4*>(kvb + static_cast<long long>(key) * 2 * kD + kD);
     float f[8];
-    unpack8(__ldg(vr + lane), f);
-    const float pa = s_sc[lane >> 2][key];
+    if (lane < kUnits) {
+      unpack8(__ldg(vr + lane), f);
+      const float pa = s_sc[lane >> 2][key];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) oa[i] += pa * f[i];
+      for (int i = 0; i < 8; ++i) oa[i] += pa * f[i];
+    }
     if (lane < kUnits - 32) {
       unpack8(__ldg(vr + 32 + lane), f);
       const float pb = s_sc[8 + (lane >> 2)][key];
@@ -565,12 +587,12 @@ __global__ void __launch_bounds__(384) k_dec_cross_attn(DecoderStep st, const __
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    s_part[warp][lane * 8 + i] = oa[i];
+    if (lane < kUnits) s_part[warp][lane * 8 + i] = oa[i];
     if (lane < kUnits - 32) s_part[warp][(32 + lane) * 8 + i] = ob[i];
   }
   __syncthreads();
   {
-    const int d = threadIdx.x;  // 384 threads = 384 output dims
+    const int d = threadIdx.x;  // kD threads = kD output dims
     float acc = 0.f;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) acc += s_part[w][d];
@@ -761,6 +783,7 @@ __global__ void k_argmax(const float* __restrict__ logits, int rows, int n_cls, 
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }  // ties -> lowest index (at::max on CPU)
   }
+  if (bi >= n_cls) bi = 0;  // all-NaN row: no comparison succeeded (the id is used as a table index downstream)
   if (lane == 0) {
     if (ids != nullptr) ids[static_cast<long long>(row) * ids_stride] = bi;
     if (next != nullptr) next[static_cast<long long>(row) * next_stride] = forced ? forced[static_cast<long long>(row) * forced_stride] : bi;
@@ -804,7 +827,8 @@ cudaError_t layernorm(const float* x, int rows, int D, const float* gamma, const
   if (rows <= 0) return cudaSuccess;
   const int grid = (rows + 7) / 8;
   if (D == 384) k_layernorm<12><<<grid, 256, 0, s>>>(x, rows, gamma, beta, eps, ob, of, rows_mod);
-  else { set_error("layernorm: unsupported width (PARSeq-base, D = 384, only)"); return cudaErrorInvalidValue; }
+  else if (D == 192) k_layernorm<6><<<grid, 256, 0, s>>>(x, rows, gamma, beta, eps, ob, of, rows_mod);
+  else { set_error("layernorm: unsupported width (PARSeq-base D = 384 or PARSeq-tiny D = 192)"); return cudaErrorInvalidValue; }
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -829,8 +853,9 @@ cudaError_t attention_enc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int crop
 cudaError_t dec_context(const int* tokens, const float* embed, const float* posq, const float* g, const float* b,
                         float eps, int pos, int n, int D, int L, __nv_bfloat16* out, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
-  if (D != 384) { set_error("dec_context: unsupported width"); return cudaErrorInvalidValue; }
-  k_dec_context<12><<<(n + 7) / 8, 256, 0, s>>>(tokens, embed, posq, g, b, eps, pos, n, L, out);
+  if (D == 384) k_dec_context<12><<<(n + 7) / 8, 256, 0, s>>>(tokens, embed, posq, g, b, eps, pos, n, L, out);
+  else if (D == 192) k_dec_context<6><<<(n + 7) / 8, 256, 0, s>>>(tokens, embed, posq, g, b, eps, pos, n, L, out);
+  else { set_error("dec_context: unsupported width"); return cudaErrorInvalidValue; }
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }
@@ -869,15 +894,19 @@ cudaError_t dec_self_attn(const DecoderStep& st, const float* q_table, const flo
 cudaError_t dec_cross_attn(const DecoderStep& st, const __nv_bfloat16* q, const __nv_bfloat16* mem_kv,
                            __nv_bfloat16* out, cudaStream_t s) {
   if (st.n_crops <= 0) return cudaSuccess;
-  if (st.D != 384 || st.heads != 12) { set_error("dec_cross_attn: built for D = 384, 12 heads"); return cudaErrorInvalidValue; }
-  if (st.np > 1 && st.np <= 32) {
+  if (!((st.D == 384 && st.heads == 12) || (st.D == 192 && st.heads == 6))) {
+    set_error("dec_cross_attn: built for PARSeq-base (D = 384, 12 heads) and PARSeq-tiny (D = 192, 6 heads)");
+    return cudaErrorInvalidValue;
+  }
+  if (st.D == 384 && st.np > 1 && st.np <= 32) {
     constexpr int smem = 2 * 128 * kRefPitch * 2;
     TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(k_dec_attn_refine<128, false>), smem));
     k_dec_attn_refine<128, false><<<dim3(3, st.n_crops), 128, smem, s>>>(q, mem_kv, 128, st.np, nullptr, 0, st.L, 0, out);
     TT_LAUNCH_CHECK();
     return cudaSuccess;
   }
-  k_dec_cross_attn<<<dim3(st.np, st.n_crops), 384, 0, s>>>(st, q, mem_kv, out);
+  if (st.D == 384) k_dec_cross_attn<384><<<dim3(st.np, st.n_crops), 384, 0, s>>>(st, q, mem_kv, out);
+  else k_dec_cross_attn<192><<<dim3(st.np, st.n_crops), 192, 0, s>>>(st, q, mem_kv, out);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }
