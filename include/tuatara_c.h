@@ -49,6 +49,9 @@ typedef struct tt_config {
                            equally sized pages, crops of pages of any size share the recognition batch */
   int slots_per_gpu;    /* concurrent execution slots (streams + host threads) per GPU: 0 = default 2, max 4.  Two slots
                            overlap one batch's host phases with another batch's kernels (+5 %); 1 = strictly serial kernels */
+  int rectify;          /* 0 (default) = the reference's axis-aligned boundingRect crop (tuatara.cpp:416).  1 = opt-in for the
+                           TODO at tuatara.cpp:411-415: each crop is the perspective warp of its rotated box to 128 x 32
+                           (cv::getPerspectiveTransform + cv::warpPerspective semantics); boxes / bboxes are unchanged */
 } tt_config;
 
 typedef struct tt_item {
@@ -147,6 +150,11 @@ TT_API int tt_crop_resize(const tt_image* image, const int32_t* rects_xywh, int 
  * skip / U-net tensors).  out == NULL only reports dims_out = {H, W, C}.  Test entry point: not thread safe against
  * other calls on the same engine. */
 TT_API int tt_craft_tap(tt_engine* e, const char* name, float* out, long long capacity, int dims_out[3]);
+/* Rectified crops (tt_config.rectify): quads [n][4][2] fp32 = top-left, top-right, bottom-right, bottom-left corners in
+ * image coordinates (may leave the image: border pixels are replicated).  out: [n][32][128][3] u8. */
+TT_API int tt_crop_warp(const tt_image* image, const float* quads, int n, uint8_t* out);
+/* The quad tt_config.rectify uses for a RotatedRect {cx, cy, w, h, angle}: 8 floats, corner order as above. */
+TT_API int tt_rect_to_quad(const float rect[5], float quad_out[8]);
 /* PARSeq forward (tuatara.cpp:307, 26 AR steps + 1 refinement). crops: [n][32][128][3] u8.
  * forced_tokens (nullable) [n][25]: teacher-forced AR context (parity tests).
  * logits_out (nullable) [n][26][95] fp32; ids_out (nullable) [n][26] argmax (== softmax + max, :486,:103). */

@@ -272,3 +272,21 @@ def image_to_data(image: np.ndarray, craft_model, parseq_model, score_override=N
     tok = Tokenizer()
     texts = [truncate_at_eos(t) for t in tok.decode(pred)]  # :492-505
     return [dict(text=t, bbox=rotated_rect_to_tesseract_format(b)) for t, b in zip(texts, boxes)]  # :511
+
+
+# ------------------------------------------------------------------------------------------------
+# Opt-in rectification (NOT reference behaviour: the reference crops the axis-aligned boundingRect, tuatara.cpp:416;
+# its TODO at :411-415 asks for "perspective transform / rotated rectangle crop").  Test oracle of tt_config.rectify:
+# the box's vertices in the order top-left, top-right, bottom-right, bottom-left, warped to 128 x 32 by OpenCV itself.
+def rect_to_quad(rect) -> np.ndarray:
+    pts = cv2.boxPoints(rect).astype(np.float32) if not hasattr(cv2, "RotatedRect") else np.asarray(
+        cv2.RotatedRect(rect[0], rect[1], rect[2]).points(), np.float32)
+    s = pts[:, 0] + pts[:, 1]
+    d = pts[:, 1] - pts[:, 0]
+    return np.stack([pts[np.argmin(s)], pts[np.argmin(d)], pts[np.argmax(s)], pts[np.argmax(d)]]).astype(np.float32)
+
+
+def rectified_crop(image: np.ndarray, quad: np.ndarray) -> np.ndarray:
+    dst = np.array([[0, 0], [127, 0], [127, 31], [0, 31]], np.float32)
+    m = cv2.getPerspectiveTransform(np.asarray(quad, np.float32), dst)
+    return cv2.warpPerspective(image, m, (128, 32), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)

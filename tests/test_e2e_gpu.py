@@ -181,3 +181,39 @@ def test_pytuatara_module_against_the_oracle(engine, weights_dir, oracle_models,
         assert got == tb.image_to_data(page, weights_dir, "outputs")   # the ctypes twin takes the same path
         n_boxes += len(got)
     assert n_boxes > 0
+
+
+def test_rectify_option_on_the_rotated_fixture(weights_dir, oracle_models):
+    """tt_config.rectify = 1 (opt-in; default 0 keeps the reference's axis-aligned crop): boxes / bboxes do not change,
+    the recogniser is fed the perspective-warped quads.  Oracle: the reference algorithm up to the final boxes, then
+    cv2.getPerspectiveTransform + warpPerspective per box and the fp32 PARSeq."""
+    from pathlib import Path
+
+    from oracle import imagemaps
+    from tuatara_b200 import _native
+
+    fx = np.load(Path(__file__).parent / "golden" / "fixture_images.npz")
+    craft, parseq = oracle_models
+    cfg = _native.tt_config()
+    tb.lib().tt_config_default(cfg)
+    cfg.rectify = 1
+    eng_r = tb.Engine(weights_dir, devices=[0], cfg=cfg)
+    eng_0 = tb.Engine(weights_dir, devices=[0])
+    try:
+        for name in ("rotated_text", "table_english"):
+            img = fx[f"{name}.img"]
+            maps = imagemaps.maps_f32(fx[f"{name}.maps_u8"])
+            got_r = eng_r.ocr_pages([img], score_override=[maps])[0]
+            got_0 = eng_0.ocr_pages([img], score_override=[maps])[0]
+            assert [g["bbox"] for g in got_r] == [g["bbox"] for g in got_0] and len(got_r) > 0
+            st = R.Stages()
+            R.image_to_data(img.copy(), craft, lambda x: torch.zeros(x.shape[0], 26, 95),
+                            score_override=(maps[..., 0], maps[..., 1]), stages=st)
+            crops = np.stack([R.rectified_crop(img, R.rect_to_quad(b)) for b in st.boxes])
+            texts = [R.truncate_at_eos(t) for t in R.Tokenizer().decode(torch.softmax(R.run_parseq(parseq, crops), -1))]
+            same = sum(g["text"] == t for g, t in zip(got_r, texts))
+            print(name, "rectified strings equal", same, "of", len(texts))
+            assert same >= 0.8 * len(texts)
+    finally:
+        eng_r.close()
+        eng_0.close()

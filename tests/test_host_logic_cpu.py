@@ -173,3 +173,16 @@ def test_tokenizer_reference_binary_live(native_lib):
         want = build_ref.decode(logits)
         assert [R.truncate_at_eos(t) for t in tok.decode(torch.softmax(torch.from_numpy(logits), -1))] == want
         assert tb.decode_ids(ids.astype(np.int32)) == want
+
+
+def test_rectify_quad_order_matches_oracle(native_lib):
+    """tt_config.rectify (opt-in, the TODO at tuatara.cpp:411-415): the corner order fed to the warp equals the oracle's
+    (float32 x + y / y - x extrema of cv2's RotatedRect.points, first index on ties), axis-aligned rects included."""
+    import tuatara_b200 as tb
+    from oracle import tuatara_ref as R
+
+    rng = np.random.default_rng(11)
+    for _ in range(3000):
+        ang = float(rng.choice([rng.uniform(-90, 90), 0.0, 90.0, -90.0, 45.0, -45.0]))
+        rect = ((float(rng.uniform(20, 1200)), float(rng.uniform(20, 1200))), (float(rng.uniform(2, 400)), float(rng.uniform(2, 90))), ang)
+        assert np.array_equal(tb.rect_to_quad(rect), R.rect_to_quad(rect)), rect

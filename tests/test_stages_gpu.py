@@ -132,3 +132,38 @@ def test_crop_resize_synth_page(native_lib):
     ref = np.stack([R.crop_to_parseq_u8(swapped, r) for r in rects])
     got = tb.crop_resize(img, rects)
     assert np.array_equal(got, ref)
+
+
+def test_crop_warp_matches_cv2_warp_perspective(native_lib):
+    """Opt-in rectified crops (tt_config.rectify): the warp kernel against cv2.getPerspectiveTransform +
+    cv2.warpPerspective(INTER_LINEAR, BORDER_REPLICATE).  The kernel restates OpenCV's sampling (double coordinates
+    rounded to 1/32 pixel, 15-bit bilinear weights), so pixels are identical unless a coordinate lands within rounding
+    noise of a 1/32-pixel boundary (the 8 x 8 solve differs in the last bits).  Measured on B200: 99.999 % identical, worst 5.  Bar: >= 99.99 % of the pixels identical,
+    no pixel off by more than 8 grey levels, mean |diff| <= 0.001."""
+    from pathlib import Path
+
+    fx = np.load(Path(__file__).parent / "golden" / "fixture_images.npz")
+    rng = np.random.default_rng(5)
+    cases = []
+    page = synth.synth_page(2)
+    for _ in range(120):
+        rect = ((float(rng.uniform(100, 1180)), float(rng.uniform(100, 1180))), (float(rng.uniform(20, 300)), float(rng.uniform(8, 70))),
+                float(rng.uniform(-90, 90)))
+        cases.append((page, R.rect_to_quad(rect)))
+    rot = fx["rotated_text.img"]
+    for _ in range(40):   # quads that leave the small rotated fixture page: border replication
+        rect = ((float(rng.uniform(0, 275)), float(rng.uniform(0, 206))), (float(rng.uniform(30, 250)), float(rng.uniform(10, 60))),
+                float(rng.uniform(-60, 60)))
+        cases.append((rot, R.rect_to_quad(rect)))
+    exact = total = 0
+    worst, sad = 0, 0.0
+    for img in (page, rot):
+        quads = [q for im, q in cases if im is img]
+        got = tb.crop_warp(img, np.stack(quads))
+        for g, q in zip(got, quads):
+            ref = R.rectified_crop(img, q)
+            d = np.abs(g.astype(np.int32) - ref.astype(np.int32))
+            exact += int((d == 0).sum()); total += d.size
+            worst = max(worst, int(d.max())); sad += float(d.sum())
+    print(f"crop_warp vs cv2: {exact / total:.5f} identical, worst {worst}, mean |diff| {sad / total:.5f}")
+    assert exact / total >= 0.9999 and worst <= 8 and sad / total <= 0.001

@@ -153,6 +153,22 @@ def crop_resize(image: np.ndarray, rects_xywh) -> np.ndarray:
     return out
 
 
+def rect_to_quad(rect) -> np.ndarray:
+    """The quadrilateral tt_config.rectify warps for a RotatedRect: float32 [4, 2] (tl, tr, br, bl)."""
+    out = np.zeros(8, np.float32)
+    check(lib().tt_rect_to_quad(ptr(_rect_array(rect)), ptr(out)), "tt_rect_to_quad")
+    return out.reshape(4, 2)
+
+
+def crop_warp(image: np.ndarray, quads) -> np.ndarray:
+    """Rectified crops on the GPU (cv2.getPerspectiveTransform + cv2.warpPerspective semantics) -> uint8 [n, 32, 128, 3]."""
+    q = np.ascontiguousarray(np.asarray(quads, np.float32).reshape(-1, 8))
+    out = np.empty((len(q), 32, 128, 3), np.uint8)
+    im = _native.image_struct(image)
+    check(lib().tt_crop_warp(C.byref(im), ptr(q), len(q), ptr(out)), "tt_crop_warp")
+    return out
+
+
 # --------------------------------------------------------------------------------- engine
 class Engine:
     """Weights resident on the GPU(s) + streams + workspaces (tt_engine_*)."""

@@ -25,7 +25,7 @@ class tt_image(C.Structure):
 class tt_config(C.Structure):
     _fields_ = [("canvas_size", C.c_float), ("mag_ratio", C.c_float), ("text_threshold", C.c_float),
                 ("link_threshold", C.c_float), ("low_text", C.c_float), ("min_area", C.c_int),
-                ("max_batch_pages", C.c_int), ("slots_per_gpu", C.c_int)]
+                ("max_batch_pages", C.c_int), ("slots_per_gpu", C.c_int), ("rectify", C.c_int)]
 
 
 class tt_ocr_options(C.Structure):
@@ -76,6 +76,8 @@ SIGNATURES = {
     "tt_postprocess": (_I, [_P, _I, _I, C.POINTER(tt_config), _P, _P, _I, _PI, _P, _P, _I, _PI]),
     "tt_crop_resize": (_I, [C.POINTER(tt_image), _P, _I, _P]),
     "tt_craft_tap": (_I, [_P, C.c_char_p, _P, C.c_longlong, _P]),
+    "tt_crop_warp": (_I, [C.POINTER(tt_image), _P, _I, _P]),
+    "tt_rect_to_quad": (_I, [_P, _P]),
     "tt_parseq_forward": (_I, [_P, _P, _I, _P, _P, _P]),
     "tt_decode": (_I, [_P, _I, _I, _P, _I]),
     "tt_tokenizer_table": (_I, [C.c_char_p, _PI, _PI, _PI]),

@@ -71,6 +71,7 @@ void tt_config_default(tt_config* cfg) {
   cfg->min_area = 10;
   cfg->max_batch_pages = 0;
   cfg->slots_per_gpu = 0;
+  cfg->rectify = 0;
 }
 
 const char* tt_last_error(void) { return last_error(); }
@@ -197,6 +198,43 @@ int tt_crop_resize(const tt_image* image, const int32_t* rects_xywh, int n, uint
     TT_CUDA_INT(dout.alloc(out_bytes));
     TT_TRY_INT(crop_resize(dpages.as<PageRef>(), dboxes.as<CropBox>(), n, dout.as<uint8_t>(), nullptr, 0));
     TT_CUDA_INT(cudaMemcpy(out, dout.p, out_bytes, cudaMemcpyDeviceToHost));
+    return 0;
+  });
+}
+
+int tt_crop_warp(const tt_image* image, const float* quads, int n, uint8_t* out) {
+  return guarded([&]() -> int {
+    if (!image || !image->data || image->channels != 3 || !quads || !out) { set_error("tt_crop_warp: need a 3-channel image, quads and an output"); return 1; }
+    if (n <= 0) return 0;
+    DevBuf src, dpages, dboxes, dout;
+    const size_t src_bytes = image->step * image->rows;
+    TT_CUDA_INT(src.alloc(src_bytes));
+    TT_CUDA_INT(cudaMemcpy(src.p, image->data, src_bytes, cudaMemcpyHostToDevice));
+    PageRef pr{src.as<uint8_t>(), image->rows, image->cols, image->step};
+    TT_CUDA_INT(dpages.alloc(sizeof(PageRef)));
+    TT_CUDA_INT(cudaMemcpy(dpages.p, &pr, sizeof(pr), cudaMemcpyHostToDevice));
+    std::vector<WarpBox> boxes(n);
+    for (int i = 0; i < n; ++i) {
+      Pt2f q[4];
+      for (int k = 0; k < 4; ++k) q[k] = Pt2f{quads[8 * i + 2 * k], quads[8 * i + 2 * k + 1]};
+      boxes[i].page = quad_to_warp(q, boxes[i].m) ? 0 : -1;
+      boxes[i].pad_ = 0;
+    }
+    TT_CUDA_INT(dboxes.alloc(sizeof(WarpBox) * n));
+    TT_CUDA_INT(cudaMemcpy(dboxes.p, boxes.data(), sizeof(WarpBox) * n, cudaMemcpyHostToDevice));
+    const size_t out_bytes = static_cast<size_t>(n) * 32 * 128 * 3;
+    TT_CUDA_INT(dout.alloc(out_bytes));
+    TT_TRY_INT(crop_warp(dpages.as<PageRef>(), dboxes.as<WarpBox>(), n, dout.as<uint8_t>(), nullptr, 0));
+    TT_CUDA_INT(cudaMemcpy(out, dout.p, out_bytes, cudaMemcpyDeviceToHost));
+    return 0;
+  });
+}
+
+int tt_rect_to_quad(const float rect[5], float quad_out[8]) {
+  return guarded([&]() -> int {
+    Pt2f q[4];
+    rect_to_quad(RotatedRect{rect[0], rect[1], rect[2], rect[3], rect[4]}, q);
+    for (int k = 0; k < 4; ++k) { quad_out[2 * k] = q[k].x; quad_out[2 * k + 1] = q[k].y; }
     return 0;
   });
 }

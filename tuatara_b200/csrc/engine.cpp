@@ -179,6 +179,8 @@ int detect_unit(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const
   // host: rescale boxes, bounding rects, output bboxes (tuatara.cpp:406-418, :256-274)
   const float inv = 1.f / ratio;  // ratio_w == ratio_h (tuatara.cpp:360-361)
   std::vector<CropBox> crops;
+  std::vector<WarpBox> warps;   // cfg.rectify: one perspective warp per box instead of the axis-aligned crop
+  const bool rectify = cfg.rectify != 0;
   for (int b = 0; b < nb; ++b) {
     PageOut& po = (*results)[u.pages[b]];
     const tt_image& im = pages[u.pages[b]];
@@ -192,6 +194,13 @@ int detect_unit(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const
       const int x0 = std::max(r.x, 0), y0 = std::max(r.y, 0);
       const int x1 = std::min(r.x + r.w, im.cols), y1 = std::min(r.y + r.h, im.rows);
       crops.push_back(CropBox{b, x0, y0, std::max(x1 - x0, 0), std::max(y1 - y0, 0)});
+      if (rectify) {
+        Pt2f quad[4];
+        rect_to_quad(adj, quad);
+        WarpBox wb{};
+        wb.page = quad_to_warp(quad, wb.m) ? b : -1;
+        warps.push_back(wb);
+      }
       pend->owner.push_back(CropOwner{u.pages[b], k++});
     }
     po.text.resize(po.bbox.size());   // zero boxes: the reference crashes in torch::cat({}) (tuatara.cpp:485); we return no items
@@ -212,7 +221,15 @@ int detect_unit(DeviceCtx& d, const tt_config& cfg, const tt_image* pages, const
   E_CUDA(cudaMemcpyAsync(boxes_dev, crops.data(), sizeof(CropBox) * n, cudaMemcpyHostToDevice, d.stream));
   g_h2d_bytes += sizeof(PageRef) * nb + sizeof(CropBox) * n;
   stage_begin(d.stream);
-  E_TRY(crop_resize(refs_dev, boxes_dev, n, nullptr, d.patch_buf + have * 128 * 96, d.stream));
+  if (rectify) {
+    WarpBox* warps_dev = d.arena.get<WarpBox>(n);
+    if (!warps_dev) { set_error("arena exhausted (warps)"); return 1; }
+    E_CUDA(cudaMemcpyAsync(warps_dev, warps.data(), sizeof(WarpBox) * n, cudaMemcpyHostToDevice, d.stream));
+    g_h2d_bytes += sizeof(WarpBox) * n;
+    E_TRY(crop_warp(refs_dev, warps_dev, n, nullptr, d.patch_buf + have * 128 * 96, d.stream));
+  } else {
+    E_TRY(crop_resize(refs_dev, boxes_dev, n, nullptr, d.patch_buf + have * 128 * 96, d.stream));
+  }
   double src = 0;
   for (const CropBox& c : crops) src += 3.0 * c.w * c.h;
   stage_end(d.stream, "crop_resize", 0.0, src + static_cast<double>(n) * 128 * 96 * 2);  // source rect + bf16 patch rows

@@ -296,6 +296,66 @@ RotatedRect adjust_rect(const RotatedRect& rr, float ratio_w, float ratio_h, flo
   return min_area_rect_f(c, 4);              // :248
 }
 
+void rect_to_quad(const RotatedRect& r, Pt2f quad[4]) {
+  Pt2f v[4];
+  rect_points(r, v);
+  int tl = 0, br = 0, tr = 0, bl = 0;
+  for (int i = 1; i < 4; ++i) {   // float32 sums / differences, first extremum wins (numpy argmin / argmax)
+    const float s = v[i].x + v[i].y, d = v[i].y - v[i].x;
+    if (s < v[tl].x + v[tl].y) tl = i;
+    if (s > v[br].x + v[br].y) br = i;
+    if (d < v[tr].y - v[tr].x) tr = i;
+    if (d > v[bl].y - v[bl].x) bl = i;
+  }
+  quad[0] = v[tl]; quad[1] = v[tr]; quad[2] = v[br]; quad[3] = v[bl];
+}
+
+bool quad_to_warp(const Pt2f q[4], double m_inv[9]) {
+  // cv::getPerspectiveTransform: 8 x 8 system in double, LU with partial pivoting
+  static const double dx[4] = {0.0, 127.0, 127.0, 0.0}, dy[4] = {0.0, 0.0, 31.0, 31.0};
+  double a[8][9];
+  for (int i = 0; i < 4; ++i) {
+    const double sx = q[i].x, sy = q[i].y;
+    double* r0 = a[i];
+    double* r1 = a[i + 4];
+    r0[0] = sx; r0[1] = sy; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = -sx * dx[i]; r0[7] = -sy * dx[i]; r0[8] = dx[i];
+    r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = sx; r1[4] = sy; r1[5] = 1; r1[6] = -sx * dy[i]; r1[7] = -sy * dy[i]; r1[8] = dy[i];
+  }
+  for (int c = 0; c < 8; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 8; ++r)
+      if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+    if (fabs(a[piv][c]) < 1e-12) return false;
+    if (piv != c)
+      for (int k = 0; k < 9; ++k) std::swap(a[piv][k], a[c][k]);
+    for (int r = c + 1; r < 8; ++r) {
+      const double f = a[r][c] / a[c][c];
+      for (int k = c; k < 9; ++k) a[r][k] -= f * a[c][k];
+    }
+  }
+  double m[9];
+  for (int r = 7; r >= 0; --r) {
+    double v = a[r][8];
+    for (int k = r + 1; k < 8; ++k) v -= a[r][k] * m[k];
+    m[r] = v / a[r][r];
+  }
+  m[8] = 1.0;
+  // cv::invert of the 3 x 3 (cofactors / determinant), as warpPerspective does before sampling
+  const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+  if (det == 0.0) return false;
+  const double id = 1.0 / det;
+  m_inv[0] = (m[4] * m[8] - m[5] * m[7]) * id;
+  m_inv[1] = (m[2] * m[7] - m[1] * m[8]) * id;
+  m_inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+  m_inv[3] = (m[5] * m[6] - m[3] * m[8]) * id;
+  m_inv[4] = (m[0] * m[8] - m[2] * m[6]) * id;
+  m_inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  m_inv[6] = (m[3] * m[7] - m[4] * m[6]) * id;
+  m_inv[7] = (m[1] * m[6] - m[0] * m[7]) * id;
+  m_inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  return true;
+}
+
 void rect_to_bbox(const RotatedRect& rr, float out[4]) {
   Pt2f v[4];
   rect_points(rr, v);                        // tuatara.cpp:258

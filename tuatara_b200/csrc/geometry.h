@@ -38,6 +38,12 @@ bool component_rect(const CompIn& c, const int* row_xmin_xmax, int img_w, int im
 
 // tuatara.cpp:236-253 for one box: corners *= (ratio * ratio_net) in fp32, minAreaRect of the 4 corners.
 RotatedRect adjust_rect(const RotatedRect& r, float ratio_w, float ratio_h, float ratio_net);
+// Opt-in rectification (the TODO at tuatara.cpp:411-415; tt_config.rectify): the box's 4 vertices ordered
+// top-left, top-right, bottom-right, bottom-left (smallest / largest x + y, smallest / largest y - x, first index wins)
+void rect_to_quad(const RotatedRect& r, Pt2f quad[4]);
+// cv::getPerspectiveTransform(quad -> {(0,0),(127,0),(127,31),(0,31)}) followed by the inversion cv::warpPerspective
+// does: m_inv maps an output pixel of the 128 x 32 crop to source coordinates.  false: degenerate quad.
+bool quad_to_warp(const Pt2f quad[4], double m_inv[9]);
 // tuatara.cpp:256-274: [min_x, min_y, max_x, max_y] of the 4 vertices, std::round-ed.
 void rect_to_bbox(const RotatedRect& r, float out[4]);
 

@@ -129,6 +129,51 @@ __global__ void __launch_bounds__(128) k_crop(const PageRef* __restrict__ pages,
   }
 }
 
+// grid (32, n), 128 threads: one output row of one crop per block, as k_crop.  Arithmetic follows
+// cv::warpPerspective's block loop (64 x 16 blocks for a 128 x 32 destination): X0 = M0*x + M1*y + M2 at the block
+// origin, then (X0 + M0*x1) * (32 / W) per pixel, no fused multiply-add (the CPU code has none either).
+__global__ void __launch_bounds__(128) k_crop_warp(const PageRef* __restrict__ pages, const WarpBox* __restrict__ boxes,
+                                                   uint8_t* __restrict__ out_u8, __nv_bfloat16* __restrict__ out_patch) {
+  const int dy = blockIdx.x, b = blockIdx.y, dx = threadIdx.x;
+  const WarpBox box = boxes[b];
+  int val[3] = {0, 0, 0};
+  if (box.page >= 0) {
+    const PageRef pg = pages[box.page];
+    const double xb = static_cast<double>(dx & ~63), x1 = static_cast<double>(dx & 63), yy = static_cast<double>(dy);
+    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(box.m[0], xb), __dmul_rn(box.m[1], yy)), box.m[2]);
+    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(box.m[3], xb), __dmul_rn(box.m[4], yy)), box.m[5]);
+    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(box.m[6], xb), __dmul_rn(box.m[7], yy)), box.m[8]);
+    double W = __dadd_rn(W0, __dmul_rn(box.m[6], x1));
+    W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
+    const double fX = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(X0, __dmul_rn(box.m[0], x1)), W)));
+    const double fY = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(Y0, __dmul_rn(box.m[3], x1)), W)));
+    const int X = __double2int_rn(fX), Y = __double2int_rn(fY);   // saturate_cast<int>: round half to even
+    // remap stores the integer parts as shorts (saturate_cast<short>)
+    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+    const int fx = X & 31, fy = Y & 31;
+    const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+    const int xa = min(max(sx, 0), pg.cols - 1), xc = min(max(sx + 1, 0), pg.cols - 1);
+    const int ya = min(max(sy, 0), pg.rows - 1), yc = min(max(sy + 1, 0), pg.rows - 1);
+    const uint8_t* r0 = pg.data + static_cast<size_t>(ya) * pg.step;
+    const uint8_t* r1 = pg.data + static_cast<size_t>(yc) * pg.step;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int v = r0[xa * 3 + c] * w00 + r0[xc * 3 + c] * w01 + r1[xa * 3 + c] * w10 + r1[xc * 3 + c] * w11;
+      val[c] = (v + (1 << 14)) >> 15;
+    }
+  }
+  if (out_u8 != nullptr) {
+    uint8_t* o = out_u8 + ((static_cast<size_t>(b) * 32 + dy) * 128 + dx) * 3;
+    o[0] = static_cast<uint8_t>(val[0]); o[1] = static_cast<uint8_t>(val[1]); o[2] = static_cast<uint8_t>(val[2]);
+  }
+  if (out_patch != nullptr) {
+    const size_t row = static_cast<size_t>(b) * 128 + (dy >> 2) * 16 + (dx >> 3);
+    __nv_bfloat16* o = out_patch + row * 96 + (dy & 3) * 8 + (dx & 7);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c * 32] = __float2bfloat16(static_cast<float>(val[c]));
+  }
+}
+
 }  // namespace
 
 cudaError_t page_resize_pad(const uint8_t* src, int src_h, int src_w, size_t src_step, uint8_t* dst, int th, int tw,
@@ -151,6 +196,14 @@ cudaError_t crop_resize(const PageRef* pages_dev, const CropBox* boxes_dev, int 
                         __nv_bfloat16* out_patches, cudaStream_t s) {
   if (n_boxes <= 0) return cudaSuccess;
   k_crop<<<dim3(32, n_boxes), 128, 0, s>>>(pages_dev, boxes_dev, out_u8, out_patches);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t crop_warp(const PageRef* pages_dev, const WarpBox* boxes_dev, int n_boxes, uint8_t* out_u8,
+                      __nv_bfloat16* out_patches, cudaStream_t s) {
+  if (n_boxes <= 0) return cudaSuccess;
+  k_crop_warp<<<dim3(32, n_boxes), 128, 0, s>>>(pages_dev, boxes_dev, out_u8, out_patches);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -34,4 +34,15 @@ struct PageRef {
 cudaError_t crop_resize(const PageRef* pages_dev, const CropBox* boxes_dev, int n_boxes, uint8_t* out_u8,
                         __nv_bfloat16* out_patches, cudaStream_t s);
 
+// Opt-in rectified crops (tt_config.rectify; the TODO at tuatara.cpp:411-415): every crop is the 128 x 32 perspective
+// warp of its box's quadrilateral, sampled the way cv::warpPerspective(INTER_LINEAR, BORDER_REPLICATE) samples it
+// (source coordinates in double, rounded to 1/32 pixel, 15-bit fixed-point bilinear weights).
+struct WarpBox {
+  int page;        // index into the page table; < 0 -> black crop
+  int pad_;
+  double m[9];     // output pixel (x, y, 1) -> source (X, Y, W), the inverted cv::getPerspectiveTransform matrix
+};
+cudaError_t crop_warp(const PageRef* pages_dev, const WarpBox* boxes_dev, int n_boxes, uint8_t* out_u8,
+                      __nv_bfloat16* out_patches, cudaStream_t s);
+
 }  // namespace tt
