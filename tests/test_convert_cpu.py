@@ -33,3 +33,22 @@ def test_dataparallel_prefix_and_bad_file(oracle_models, tmp_path):
         assert "not the expected architecture" in str(e)
     else:
         raise AssertionError("a foreign state_dict must be rejected")
+
+
+def test_parseq_torchscript_archive_and_pickle_policy(oracle_models, tmp_path):
+    """PARSeq as the reference ships it (a TorchScript archive under the file name of tuatara.cpp:423) converts to the
+    same bytes as the direct export; a pickled nn.Module (arbitrary code on load) is refused unless explicitly trusted."""
+    import pytest
+
+    craft, parseq = oracle_models
+    torch.jit.trace(craft, torch.zeros(1, 3, 64, 64), check_trace=False).save(str(tmp_path / convert.CRAFT_FILE))
+    torch.jit.trace(parseq, torch.zeros(1, 3, 32, 128), check_trace=False).save(str(tmp_path / convert.PARSEQ_FILE))
+    assert convert.main(["--weights-dir", str(tmp_path)]) == 0
+    weights.export_parseq(parseq.state_dict(), tmp_path / "parseq_direct.ttw")
+    assert _same_file(tmp_path / "parseq.ttw", tmp_path / "parseq_direct.ttw")
+    # a whole pickled module: weights_only refuses it
+    mod = tmp_path / "module.pkl"
+    torch.save(craft, mod)
+    with pytest.raises(ValueError, match="unsafe"):
+        convert.load_state_dict(mod)
+    assert set(convert.load_state_dict(mod, unsafe_pickle=True)) == set(craft.state_dict())

@@ -228,6 +228,27 @@ def test_parseq_tiny_variant(oracle_models):
         eng.close()
 
 
+def test_converted_torchscript_weights_run_identically(engine, oracle_models, tmp_path):
+    """the reference's two weight files (TorchScript archives, tuatara.cpp:333 / :423) through
+    tuatara_b200.convert, loaded by a second engine: logits and ids equal those of the directly exported weights."""
+    from tuatara_b200 import convert
+
+    craft, parseq = oracle_models
+    torch.jit.trace(craft, torch.zeros(1, 3, 64, 64), check_trace=False).save(str(tmp_path / convert.CRAFT_FILE))
+    torch.jit.trace(parseq, torch.zeros(1, 3, 32, 128), check_trace=False).save(str(tmp_path / convert.PARSEQ_FILE))
+    assert convert.main(["--weights-dir", str(tmp_path)]) == 0
+    eng2 = tb.Engine(str(tmp_path), devices=[0])
+    try:
+        crops = _crops(24, seed=11)
+        l1, i1 = engine.parseq_forward(crops)
+        l2, i2 = eng2.parseq_forward(crops)
+        assert np.array_equal(i1, i2) and np.array_equal(l1, l2)
+        craft_in, _ = tb.preprocess(synth.synth_page(5)[:320, :384])
+        assert np.array_equal(engine.craft_forward(craft_in), eng2.craft_forward(craft_in))
+    finally:
+        eng2.close()
+
+
 def test_decode_matches_reference_tokenizer(native_lib):
     rng = np.random.default_rng(0)
     tok = R.Tokenizer()

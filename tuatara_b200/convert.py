@@ -24,14 +24,22 @@ CRAFT_FILE = "craft_traced_torchscript_model.pt"   # tuatara.cpp:333
 PARSEQ_FILE = "parseq_torchscript.bin"              # tuatara.cpp:423
 
 
-def load_state_dict(path: str | Path) -> dict:
-    """state_dict of a TorchScript archive, a pickled module, or a pickled (possibly nested) state_dict."""
+def load_state_dict(path: str | Path, unsafe_pickle: bool = False) -> dict:
+    """state_dict of a TorchScript archive or a pickled (possibly nested) state_dict.  Plain pickles are read with
+    ``weights_only=True`` (tensors and containers only); a file that needs arbitrary unpickling -- a pickled nn.Module,
+    i.e. code execution on load -- is refused unless ``unsafe_pickle`` (CLI: --unsafe-pickle) says the file is trusted."""
     path = str(path)
     try:
         return dict(torch.jit.load(path, map_location="cpu").state_dict())
     except (RuntimeError, ValueError):
         pass
-    obj = torch.load(path, map_location="cpu", weights_only=False)
+    try:
+        obj = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as exc:  # noqa: BLE001  (pickle.UnpicklingError and friends)
+        if not unsafe_pickle:
+            raise ValueError(f"{path}: not a TorchScript archive or a tensors-only pickle ({exc}); "
+                             "pass unsafe_pickle=True / --unsafe-pickle only for files you trust") from exc
+        obj = torch.load(path, map_location="cpu", weights_only=False)
     if hasattr(obj, "state_dict"):
         return dict(obj.state_dict())
     for key in ("state_dict", "model", "net"):
@@ -51,11 +59,12 @@ def normalise(sd: dict, anchor: str) -> dict:
     return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
 
 
-def convert(craft_path, parseq_path, out_dir) -> str:
+def convert(craft_path, parseq_path, out_dir, unsafe_pickle: bool = False) -> str:
     out = Path(out_dir)
     out.mkdir(parents=True, exist_ok=True)
-    weights.export_craft(normalise(load_state_dict(craft_path), "basenet.slice1.0.weight"), out / "craft.ttw")
-    weights.export_parseq(normalise(load_state_dict(parseq_path), "encoder.patch_embed.proj.weight"), out / "parseq.ttw")
+    weights.export_craft(normalise(load_state_dict(craft_path, unsafe_pickle), "basenet.slice1.0.weight"), out / "craft.ttw")
+    weights.export_parseq(normalise(load_state_dict(parseq_path, unsafe_pickle), "encoder.patch_embed.proj.weight"),
+                          out / "parseq.ttw")
     return str(out)
 
 
@@ -65,6 +74,8 @@ def main(argv=None) -> int:
     ap.add_argument("--craft")
     ap.add_argument("--parseq")
     ap.add_argument("--out")
+    ap.add_argument("--unsafe-pickle", action="store_true",
+                    help="allow full unpickling (executes code in the file): only for checkpoints you trust")
     a = ap.parse_args(argv)
     if a.weights_dir:
         a.craft = a.craft or str(Path(a.weights_dir) / CRAFT_FILE)
@@ -72,7 +83,7 @@ def main(argv=None) -> int:
         a.out = a.out or a.weights_dir
     if not (a.craft and a.parseq and a.out):
         ap.error("give --weights-dir, or --craft, --parseq and --out")
-    print(convert(a.craft, a.parseq, a.out))
+    print(convert(a.craft, a.parseq, a.out, a.unsafe_pickle))
     return 0
 
 

@@ -34,6 +34,8 @@ bool WeightFile::load(const std::string& path, std::vector<int>* meta_out) {
   if (size < 8 || std::memcmp(buf.data(), "TTW1", 4) != 0) { set_error("bad weight file " + path); return false; }
   uint32_t n;
   std::memcpy(&n, buf.data() + 4, 4);
+  // the directory must lie inside the file before anything in it is trusted
+  if (static_cast<uint64_t>(n) > (size - 8) / 120) { set_error("bad weight file " + path + " (directory larger than the file)"); return false; }
   if (cudaMalloc(&arena_, size) != cudaSuccess) { set_error("cudaMalloc failed for " + path); return false; }
   if (cudaMemcpy(arena_, buf.data(), size, cudaMemcpyHostToDevice) != cudaSuccess) {
     set_error("weight upload failed for " + path);
@@ -50,16 +52,18 @@ bool WeightFile::load(const std::string& path, std::vector<int>* meta_out) {
     std::memcpy(dims, e + 72, 32);
     std::memcpy(&off, e + 104, 8);
     std::memcpy(&nb, e + 112, 8);
-    if (off + nb > size) { set_error("truncated weight file " + path); return false; }
+    if (off > size || nb > size - off) { set_error("truncated weight file " + path); return false; }   // no uint64 wrap
+    if (dt > 2 || nd > 4 || off % 16 != 0) { set_error("bad weight file " + path + " (tensor '" + name + "')"); return false; }
+    if (meta_out && std::strcmp(name, "meta") == 0) {
+      if (nb % 4 != 0) { set_error("bad weight file " + path + " (meta tensor)"); return false; }
+      meta_out->resize(nb / 4);
+      std::memcpy(meta_out->data(), buf.data() + off, nb);
+    }
     WTensor t;
     t.ptr = static_cast<char*>(arena_) + off;
     t.dtype = static_cast<int>(dt);
     t.nbytes = nb;
     for (uint32_t k = 0; k < nd; ++k) t.dims.push_back(static_cast<long long>(dims[k]));
-    if (meta_out && std::strcmp(name, "meta") == 0) {
-      meta_out->resize(nb / 4);
-      std::memcpy(meta_out->data(), buf.data() + off, nb);
-    }
     t_[name] = t;
   }
   return true;
