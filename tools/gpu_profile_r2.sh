@@ -1,0 +1,22 @@
+#!/bin/bash
+# Round-2 ncu evidence for profiles/: launch list of a short bench run + --set full captures of the dominant kernels
+# (LayerNorm-fused GEMM pair, fused decoder kernels, cross attention, conv1_2).  Numbers under ncu are never bench values.
+mkdir -p gpurun_out
+TAG=${1:-r2}
+export TT_BENCH_CHILD=1   # profile the bench process itself, not the supervisor's child
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 6000 --csv \
+  --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 1 --pages-per-gpu 8 --batch-pages 8 --no-cpu-baseline --no-configs > gpurun_out/ncu_bench_$TAG.log 2>&1
+echo "launch list rc=$?"
+# producer proj-like (K 384) + consumer fc1 (GELU); producer fc2-like (K 1536) + consumer qkv
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 4 -c 2 -f \
+  -o gpurun_out/prof_lnpair_proj_fc1_$TAG python tools/ln_probe.py 384 1536 2 > gpurun_out/ncu_lnpair1_$TAG.log 2>&1; echo "ln pair proj+fc1 rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 4 -c 2 -f \
+  -o gpurun_out/prof_lnpair_fc2_qkv_$TAG python tools/ln_probe.py 1536 1152 0 > gpurun_out/ncu_lnpair2_$TAG.log 2>&1; echo "ln pair fc2+qkv rc=$?"
+for k in k_dec_dense k_dec_cross_attn k_dec_self_attn_ar k_attn_enc; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 60 -c 2 -f \
+    -o gpurun_out/prof_${k}_$TAG python tools/dec_bench.py 9600 > gpurun_out/ncu_${k}_$TAG.log 2>&1; echo "$k rc=$?"
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 1 -c 1 -f \
+    -o gpurun_out/prof_c1_2_$TAG python tools/conv_probe.py 8 1024 1024 64 64 2 > gpurun_out/ncu_c1_2_$TAG.log 2>&1
+echo "full capture c1_2 rc=$?"
+ls -la gpurun_out | grep $TAG
