@@ -65,6 +65,23 @@ def test_craft_per_slice_parity(engine, oracle_models):
         assert worst[name] <= bar, f"{name}: rel-L2 {worst[name]:.4f} > {bar}"
 
 
+def test_craft_fused_maxpool_is_bit_identical(engine, monkeypatch):
+    """The 2x2 max-pools run in the epilogues of conv1_2 / conv2_2 / conv3_3 / conv4_3 (halo and per-tap schedules, single
+    CTAs and CTA pairs, pooled-only and pooled + skip outputs).  Pooling the bf16-rounded values is what the separate
+    kernel did, so every activation and the maps must keep their bits; sizes with partial edge tiles included."""
+    for h, w in ((640, 768), (1024, 1024), (608, 352)):
+        craft_in, _ = tb.preprocess(synth.synth_page(6)[:h, :w])
+        fused = engine.craft_forward(craft_in)
+        taps_f = {k: engine.craft_tap(k) for k in ("relu2_2", "relu3_2", "relu4_3", "relu5_3")}
+        monkeypatch.setenv("TT_CRAFT_POOLFUSE", "0")
+        plain = engine.craft_forward(craft_in)
+        taps_p = {k: engine.craft_tap(k) for k in taps_f}
+        monkeypatch.delenv("TT_CRAFT_POOLFUSE")
+        for k in taps_f:
+            assert np.array_equal(taps_f[k], taps_p[k]), (h, w, k)
+        assert np.array_equal(fused, plain), (h, w)
+
+
 def _crops(n, seed=0):
     img = synth.synth_page(seed)
     rng = np.random.default_rng(seed)

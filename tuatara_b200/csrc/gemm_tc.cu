@@ -60,6 +60,7 @@ struct KParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
   CUtensorMap tmR, tmC;  // TMA epilogue: fp32 residual (load) and output (store), box {32 cols, 128 rows}
+  CUtensorMap tmP;       // fused 2x2 max-pool: the pooled output, box {32 ch, TW/2, 16/TW, 1}, SWIZZLE_64B
   CUtensorMap tmCb;      // LayerNorm-statistics producer: bf16 copy of the output, box {32 cols, 32 rows}, SWIZZLE_64B
   int mode;  // 0 plain rows, 1 conv tiles
   int M, N, BN, BK;
@@ -139,8 +140,10 @@ __device__ __forceinline__ long long dbg_clock(bool on) { return on ? clock64() 
 // are clipped by the TMA unit.
 // LN: LayerNorm fused away (Epilogue::ln_*).  With TE the kernel is the producer (row statistics + bf16 copy of its
 // output), with bf16 outputs it is the consumer (normalisation applied algebraically to the accumulators).
-template <int OUT, int ACT, bool RES, bool PAIR, int EW, bool TE = false, bool TS = false, bool LN = false>
+// POOL (TS conv epilogue only): 1 = write the 2x2 max-pooled tile instead of the tile, 2 = both.
+template <int OUT, int ACT, bool RES, bool PAIR, int EW, bool TE = false, bool TS = false, bool LN = false, int POOL = 0>
 __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kernel(const __grid_constant__ KParams p) {
+  static_assert(POOL == 0 || (TS && EW == 8 && !LN), "fused max-pool: bf16 TMA-store epilogue with 8 warps");
   static_assert(!TE || (OUT == OUT_F32 && RES && EW == 4), "TMA epilogue: fp32 out + residual, 4 epilogue warps");
   static_assert(!LN || TE || OUT == OUT_BF16, "LayerNorm fusion: TMA-epilogue producer or bf16-output consumer");
   constexpr int kSlot = kResSlotBytes;   // stride of the TMA-epilogue ring
@@ -166,7 +169,8 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
   uint8_t* ring = smem + (resident ? num_kb * b_bytes : 0);
   uint8_t* res_ring = ring + p.stages * stage_bytes;            // TE only
   uint8_t* ln_copy = res_ring + kResSlots * kSlot;               // TE && LN only
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(res_ring + (TE ? kResSlots * kSlot + (LN ? kLnCopyBytes : 0) : TS ? EW * kTsBufs * 2048 : 0));
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(res_ring + (TE ? kResSlots * kSlot + (LN ? kLnCopyBytes : 0)
+                                                           : TS ? EW * kTsBufs * 2048 + (POOL ? EW * kTsBufs * 512 : 0) : 0));
   (void)ln_copy;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -430,6 +434,15 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
                             : ptx::smem_u32(reinterpret_cast<uint8_t*>(ctl + 1)) + (warp - kEpiWarp0) * 2048;
     int ts_buf = 0;
     (void)ts_buf;
+    // fused 2x2 max-pool: a warp's 32 pixels are 32/TW rows of TW pixels; partners are lane ^ 1 (x) and lane ^ TW (y),
+    // the even/even lane writes pooled pixel j of the warp's 8 into a 512-byte SWIZZLE_64B tile
+    const int pool_tw = p.TW;
+    const bool pool_writer = POOL != 0 && (lane & 1) == 0 && (lane & pool_tw) == 0;
+    const int pool_j = pool_tw == 8 ? ((lane >> 4) * 4 + ((lane & 7) >> 1)) : ((lane & 15) >> 1);
+    const uint32_t pool_stg = POOL != 0 ? ptx::smem_u32(res_ring) + EW * kTsBufs * 2048 + (warp - kEpiWarp0) * kTsBufs * 512 : 0u;
+    const uint32_t pool_row = pool_stg + pool_j * 64;
+    const int pool_sw = (pool_j >> 1) & 3;
+    (void)pool_writer; (void)pool_row; (void)pool_sw;
     const uint32_t bias_s = ptx::smem_u32(&ctl->bias[0][0]);
     const uint32_t own_row = stg + lane * 64;
     const int own_sw = (lane >> 1) & 3;          // swizzle of this thread's own row
@@ -773,7 +786,20 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
                   uint4 o;
                   o.x = pack_bf16(v[8 * k + 0], v[8 * k + 1]); o.y = pack_bf16(v[8 * k + 2], v[8 * k + 3]);
                   o.z = pack_bf16(v[8 * k + 4], v[8 * k + 5]); o.w = pack_bf16(v[8 * k + 6], v[8 * k + 7]);
-                  ptx::sts128(dst_row + (((sc * 2 + k) ^ own_sw) << 4), o);
+                  if constexpr (POOL != 1) ptx::sts128(dst_row + (((sc * 2 + k) ^ own_sw) << 4), o);
+                  if constexpr (POOL != 0) {
+                    uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      uint32_t t = __shfl_xor_sync(0xffffffffu, w[e], 1);
+                      __nv_bfloat162 a = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&w[e]), *reinterpret_cast<__nv_bfloat162*>(&t));
+                      w[e] = *reinterpret_cast<uint32_t*>(&a);
+                      t = __shfl_xor_sync(0xffffffffu, w[e], pool_tw);
+                      a = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&w[e]), *reinterpret_cast<__nv_bfloat162*>(&t));
+                      w[e] = *reinterpret_cast<uint32_t*>(&a);
+                    }
+                    if (pool_writer) ptx::sts128(pool_row + ts_buf * 512 + (((sc * 2 + k) ^ pool_sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+                  }
                 }
               }
             }
@@ -782,8 +808,11 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
               __syncwarp();
               if (lane == 0) {
                 if (dbg != 1) {
-                  if (mode == 1) ptx::tma_store_4d_s(&p.tmC, stg + ts_buf * 2048, n0 + c0 * 16, ts_c1, ts_c2, ts_c3);
-                  else ptx::tma_store_2d_s(&p.tmC, stg + ts_buf * 2048, n0 + c0 * 16, ts_c1);
+                  if constexpr (POOL != 1) {
+                    if (mode == 1) ptx::tma_store_4d_s(&p.tmC, stg + ts_buf * 2048, n0 + c0 * 16, ts_c1, ts_c2, ts_c3);
+                    else ptx::tma_store_2d_s(&p.tmC, stg + ts_buf * 2048, n0 + c0 * 16, ts_c1);
+                  }
+                  if constexpr (POOL != 0) ptx::tma_store_4d_s(&p.tmP, pool_stg + ts_buf * 512, n0 + c0 * 16, ts_c1 >> 1, ts_c2 >> 1, ts_c3);
                 }
                 ptx::bulk_commit();
               }
@@ -1000,6 +1029,8 @@ int epi_warps(const Epilogue& e, int BN) {
 
 template <bool PAIR>
 void (*select_kernel_ts(const Epilogue& e, int ew))(const KParams) {
+  if (e.pool_mode == 1) return gemm_tc_kernel<OUT_BF16, ACT_RELU, false, PAIR, 8, false, true, false, 1>;
+  if (e.pool_mode == 2) return gemm_tc_kernel<OUT_BF16, ACT_RELU, false, PAIR, 8, false, true, false, 2>;
   if (e.ln_stats_in != nullptr) {   // LayerNorm consumer: plain or GELU bf16 outputs
     if (ew == 8) return e.act == ACT_GELU ? gemm_tc_kernel<OUT_BF16, ACT_GELU, false, PAIR, 8, false, true, true>
                                           : gemm_tc_kernel<OUT_BF16, ACT_NONE, false, PAIR, 8, false, true, true>;
@@ -1078,9 +1109,14 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
     if (te && kp.pair && te_pair_env == 0) te = false;
   }
   static const int ts_env = env_int("TT_GEMM_TS", 1);
-  const bool ts = !te && ts_env != 0 && kp.epi.out_type == OUT_BF16 && kp.BN % 32 == 0 && kp.epi.ldc % 8 == 0 &&
+  const bool ts = !te && (ts_env != 0 || kp.epi.pool_mode != 0) && kp.epi.out_type == OUT_BF16 && kp.BN % 32 == 0 && kp.epi.ldc % 8 == 0 &&
                   reinterpret_cast<uintptr_t>(kp.epi.out) % 16 == 0;
   const int ew = te ? 4 : epi_warps(kp.epi, kp.BN);
+  if (kp.epi.pool_mode != 0 && (!ts || kp.mode != 1 || ew != 8 || kp.epi.act != ACT_RELU || kp.epi.pool_out == nullptr || kp.H % 2 || kp.W % 2 ||
+                                kp.N % 32 != 0 || reinterpret_cast<uintptr_t>(kp.epi.pool_out) % 16 != 0)) {
+    set_error("gemm: the fused 2x2 max-pool needs a ReLU conv with bf16 TMA-store output, even H and W, Cout % 32 == 0");
+    return cudaErrorInvalidValue;
+  }
   KernelFn fn;
   const bool ln_prod = kp.epi.ln_stats_out != nullptr, ln_cons = kp.epi.ln_stats_in != nullptr;
   if (ln_prod && (!te || kp.epi.ln_xb_out == nullptr || kp.epi.ldxb % 8 != 0 || reinterpret_cast<uintptr_t>(kp.epi.ln_xb_out) % 16 != 0 || kp.num_n_tiles > 4)) {
@@ -1108,7 +1144,17 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
     }
   } else if (ts) {
     fn = kp.pair ? select_kernel_ts<true>(kp.epi, ew) : select_kernel_ts<false>(kp.epi, ew);
-    if (kp.mode == 1) {
+    if (kp.epi.pool_mode != 0) {
+      const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kp.N), static_cast<cuuint64_t>(kp.W / 2), static_cast<cuuint64_t>(kp.H / 2),
+                                  static_cast<cuuint64_t>(kp.M / (kp.H * kp.W))};
+      const cuuint64_t pitch = static_cast<cuuint64_t>(kp.N) * 2;
+      const cuuint64_t strides[3] = {pitch, pitch * (kp.W / 2), pitch * (kp.W / 2) * (kp.H / 2)};
+      const cuuint32_t box[4] = {32, static_cast<cuuint32_t>(kp.TW / 2), static_cast<cuuint32_t>(16 / kp.TW), 1};
+      if (!make_tmap_bf16(&kp.tmP, kp.epi.pool_out, 4, dims, strides, box, 64)) return cudaErrorInvalidValue;
+    }
+    if (kp.epi.pool_mode == 1) {
+      // pooled output only: no un-pooled store map
+    } else if (kp.mode == 1) {
       const cuuint64_t dims[4] = {static_cast<cuuint64_t>(kp.N), static_cast<cuuint64_t>(kp.W), static_cast<cuuint64_t>(kp.H),
                                   static_cast<cuuint64_t>(kp.M / (kp.H * kp.W))};
       const cuuint64_t pitch = static_cast<cuuint64_t>(kp.epi.ldc) * 2;
@@ -1126,7 +1172,8 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   }
   TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
   const int threads = 64 + 32 * ew + (te ? 64 : 0);
-  const int staging = te ? kResSlots * kResSlotBytes + (ln_prod ? kLnCopyBytes : 0) : ts ? ew * (ew == 16 ? 1 : 2) * 2048 : ew * 2048;
+  const int staging = te ? kResSlots * kResSlotBytes + (ln_prod ? kLnCopyBytes : 0)
+                         : ts ? ew * (ew == 16 ? 1 : 2) * (2048 + (kp.epi.pool_mode ? 512 : 0)) : ew * 2048;
   const int slots = kp.pair ? max_pairs(reinterpret_cast<const void*>(fn), 200 * 1024, threads) : num_sms();
   if (kp.b_resident && (num_kb * b_bytes > (kp.pair ? kResidentMaxPair : kp.halo ? kHaloResidentMax : kResidentMax) || kp.num_n_tiles > slots)) kp.b_resident = 0;
   const int res_bytes = kp.b_resident ? num_kb * b_bytes : 0;
@@ -1192,7 +1239,7 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
 }
 
 cudaError_t check_epilogue(const Epilogue& e, int N, int BN) {
-  if (e.out == nullptr) { set_error("gemm: null output"); return cudaErrorInvalidValue; }
+  if (e.out == nullptr && e.pool_mode != 1) { set_error("gemm: null output"); return cudaErrorInvalidValue; }
   if (e.out_type == OUT_CLS_TAIL && (BN != 16 || N != 16 || e.tail == nullptr)) {
     set_error("gemm: cls tail needs N == BN == 16 and tail weights");
     return cudaErrorInvalidValue;

@@ -28,6 +28,12 @@ struct Epilogue {
   // OUT_CLS_TAIL: after bias+ReLU on the 16 accumulators, two 1x1 convs in registers
   // (16->16 ReLU, 16->2) and an fp32 [pixel][2] store.  tail = {w4[16][16], b4[16], w5[2][16], b5[2]}
   const float* tail = nullptr;
+  // ---- 2x2 max-pool fused into a conv's bf16 epilogue (CRAFT: vgg16_bn features 6/13/23/33 follow conv1_2, conv2_2,
+  // conv3_3, conv4_3).  pool_mode 1: only the pooled tensor [B][H/2][W/2][Cout] is written (out may be null);
+  // 2: both (conv2_2's un-pooled output is a U-net skip tensor).  Pooling the bf16-rounded values equals rounding the
+  // pooled fp32 values (rounding is monotonic), so the bits are those of the separate pooling kernel.
+  __nv_bfloat16* pool_out = nullptr;
+  int pool_mode = 0;
   // ---- LayerNorm fused away (PARSeq encoder: x -> LN -> Linear).  With W' = W * gamma (folded at export),
   //   Linear(LN(x))[n] = rstd * (x . W'[n]) - rstd * mean * c1[n] + c0[n],  c1[n] = sum_k W'[n][k], c0[n] = b[n] + beta . W[n]
   // so the GEMM reads the UN-normalised row as bf16 and its epilogue applies the row's (mean, rstd).

@@ -117,8 +117,12 @@ cudaError_t DeviceCtx::craft_forward(const uint8_t* in, int B, int H, int W, flo
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4, H8 = H / 8, W8 = W / 8, H16 = H / 16, W16 = W / 16;
   cudaStream_t s = stream;
 
+  // pooled != nullptr: the 2x2 max-pool that follows the conv runs in its epilogue (out == nullptr: only the pooled
+  // tensor is written).  TT_CRAFT_POOLFUSE=0 keeps the separate pooling kernel (A/B runs).
+  const char* pool_env = std::getenv("TT_CRAFT_POOLFUSE");   // read per call: the parity test flips it in-process
+  const bool pool_fuse = !(pool_env && std::atoi(pool_env) == 0);
   auto conv = [&](const char* name, const bf* a, int Ca, const bf* b, int Cb, int hh, int ww, int taps, int dil, int cout,
-                  bool relu, bf* out) -> cudaError_t {
+                  bool relu, bf* out, bf* pooled = nullptr) -> cudaError_t {
     ConvProblem c;
     c.batch = B; c.H = hh; c.W = ww;
     c.src[0] = ConvSrc{a, Ca, Ca};
@@ -131,7 +135,19 @@ cudaError_t DeviceCtx::craft_forward(const uint8_t* in, int B, int H, int W, flo
     e.bias = w->craft.f32(std::string(name) + ".b");
     e.act = relu ? ACT_RELU : ACT_NONE;
     e.out = out; e.out_type = OUT_BF16; e.ldc = cout;
+    if (pooled) { e.pool_out = pooled; e.pool_mode = out ? 2 : 1; }
     return conv_forward(c, e, s);
+  };
+  // conv + ReLU followed by MaxPool2d(2, 2); `full` (nullable) also keeps the un-pooled tensor
+  auto conv_pool = [&](const char* name, const bf* a, int Ca, int hh, int ww, int cout, bf* full, bf* pooled) -> cudaError_t {
+    if (pool_fuse) return conv(name, a, Ca, nullptr, 0, hh, ww, 9, 1, cout, true, full, pooled);
+    bf* tmp = full;
+    if (!tmp) {
+      tmp = arena.get<bf>(static_cast<size_t>(B) * hh * ww * cout);
+      if (!tmp) { set_error("arena exhausted (conv_pool)"); return cudaErrorMemoryAllocation; }
+    }
+    if (cudaError_t e1 = conv(name, a, Ca, nullptr, 0, hh, ww, 9, 1, cout, true, tmp)) return e1;
+    return maxpool2x2(tmp, pooled, B, hh, ww, cout, s);
   };
 #define CV(...) do { cudaError_t _e = conv(__VA_ARGS__); if (_e != cudaSuccess) return _e; } while (0)
 #define RUN(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
@@ -140,32 +156,25 @@ cudaError_t DeviceCtx::craft_forward(const uint8_t* in, int B, int H, int W, flo
   RUN(page_im2col(in, B, H, W, x0, s));
   ARENA_GET(a1, bf, px * 64);
   CV("c1_1", x0, 32, nullptr, 0, H, W, 1, 1, 64, true, a1);  // 3x3 conv as a K=32 GEMM over the im2col'd pixels
-  ARENA_GET(a2, bf, px * 64);
-  CV("c1_2", a1, 64, nullptr, 0, H, W, 9, 1, 64, true, a2);
   ARENA_GET(p1, bf, px / 4 * 64);
-  RUN(maxpool2x2(a2, p1, B, H, W, 64, s));
+  RUN(conv_pool("c1_2", a1, 64, H, W, 64, nullptr, p1));
   ARENA_GET(b1, bf, px / 4 * 128);
   CV("c2_1", p1, 64, nullptr, 0, H2, W2, 9, 1, 128, true, b1);
   ARENA_GET(s1, bf, px / 4 * 128);  // relu2_2 (ReLU'd through upstream's in-place aliasing)
-  CV("c2_2", b1, 128, nullptr, 0, H2, W2, 9, 1, 128, true, s1);
   ARENA_GET(p2, bf, px / 16 * 128);
-  RUN(maxpool2x2(s1, p2, B, H2, W2, 128, s));
+  RUN(conv_pool("c2_2", b1, 128, H2, W2, 128, s1, p2));
   ARENA_GET(c1, bf, px / 16 * 256);
   CV("c3_1", p2, 128, nullptr, 0, H4, W4, 9, 1, 256, true, c1);
   ARENA_GET(s2, bf, px / 16 * 256);  // relu3_2
   CV("c3_2", c1, 256, nullptr, 0, H4, W4, 9, 1, 256, true, s2);
-  ARENA_GET(c3, bf, px / 16 * 256);
-  CV("c3_3", s2, 256, nullptr, 0, H4, W4, 9, 1, 256, true, c3);
   ARENA_GET(p3, bf, px / 64 * 256);
-  RUN(maxpool2x2(c3, p3, B, H4, W4, 256, s));
+  RUN(conv_pool("c3_3", s2, 256, H4, W4, 256, nullptr, p3));
   ARENA_GET(d1, bf, px / 64 * 512);
   CV("c4_1", p3, 256, nullptr, 0, H8, W8, 9, 1, 512, true, d1);
   ARENA_GET(s3, bf, px / 64 * 512);  // "relu4_3" (really conv4_2)
   CV("c4_2", d1, 512, nullptr, 0, H8, W8, 9, 1, 512, true, s3);
-  ARENA_GET(d3, bf, px / 64 * 512);
-  CV("c4_3", s3, 512, nullptr, 0, H8, W8, 9, 1, 512, true, d3);
   ARENA_GET(p4, bf, px / 256 * 512);
-  RUN(maxpool2x2(d3, p4, B, H8, W8, 512, s));
+  RUN(conv_pool("c4_3", s3, 512, H8, W8, 512, nullptr, p4));
   ARENA_GET(e1, bf, px / 256 * 512);
   CV("c5_1", p4, 512, nullptr, 0, H16, W16, 9, 1, 512, true, e1);
   ARENA_GET(s4, bf, px / 256 * 512);  // "relu5_3": conv5_2 + BN, NOT ReLU'd (slice5 starts with a MaxPool)
