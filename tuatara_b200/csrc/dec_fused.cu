@@ -1,18 +1,20 @@
 // Fused dense kernels of the PARSeq decoder's AR loop: see dec_fused.cuh for what they replace and why.
 //
-// Layout of one CTA (192 threads, 128 crops = 128 TMEM lanes):
+// Layout of one CTA (320 threads, 128 crops = 128 TMEM lanes):
 //   warp 0      TMA producer : the CTA's 128 input rows -> sA once, then every weight tile of the step, in a static
 //                              order, through a ring of [128 weight rows][64 k] SWIZZLE_128B units
 //   warp 1      MMA issuer   : tcgen05.mma M=128, N<=128 per unit, fp32 accumulators in TMEM
-//   warps 2..5  row owners   : thread = crop = TMEM lane.  LayerNorm / GELU / bias in registers; results go back to smem
-//                              as the next GEMM's A operand (K-major SWIZZLE_128B, written with the same XOR the TMA uses)
+//   warps 2..9  row owners   : thread = crop = TMEM lane, two warps per lane quadrant splitting a phase's columns.
+//                              LayerNorm / GELU / bias in registers; results go back to smem as the next GEMM's A operand
+//                              (K-major SWIZZLE_128B, written with the same XOR the TMA uses)
 // TMEM columns [0, D) hold the residual row t for the whole kernel: `t += x W^T` is an accumulating MMA onto those
 // columns, the fp32 input row is written there with tcgen05.st.  Columns [D, D+128) take the GEMMs whose result feeds an
-// activation (l1 chunk, head).  MMA and row-owner phases alternate; they meet on a 160-thread named barrier (A operand /
+// activation (l1 chunk, head).  MMA and row-owner phases alternate; they meet on a 288-thread named barrier (A operand /
 // TMEM ready for the tensor core) and on two mbarriers the MMA warp commits to in turn (accumulator ready for the rows).
 #include "dec_fused.cuh"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <math.h>
 
@@ -26,7 +28,8 @@ namespace tt {
 namespace {
 
 constexpr int kUnit = 16384;   // [128 rows][64 bf16]
-constexpr int kThreads = 192;
+constexpr int kRowThreads = 256;            // 8 row-owner warps: two per TMEM lane quadrant
+constexpr int kThreads = 64 + kRowThreads;  // + TMA producer warp + MMA issuer warp
 constexpr int kTmemCols = 512;
 constexpr int kMaxStages = 8;
 
@@ -35,21 +38,19 @@ enum { MODE_B = 0, MODE_A2 = 1 };
 struct DenseParams {
   CUtensorMap tm_in;                     // [n][D] bf16 activation rows of this step, box {64, 128}
   CUtensorMap tm_w0, tm_w1, tm_w2, tm_wh;
-  const float *b0, *b1, *b2, *bh;        // A2: b0 = sa.out bias, b1 = q bias.  B: ca.out, l1, l2, head biases
-  const float *lnA_g, *lnA_b;            // A2: norm1.  B: norm2
-  const float *lnF_g, *lnF_b;            // B: the decoder's final norm
-  const float* posq_row;                 // A2: pos_queries[step]
+  const float* vec_src;                  // the kernel's per-column vectors, packed in smem order (dec_dense_init): one bulk copy
   float* t_scratch;                      // [tiles][D][128]
   __nv_bfloat16* q_out;                  // A2
   float* logits;                         // B: [n][L][ncp]
   int* tokens;                           // B: [n][L]
   const int* forced;                     // B: [n][L-1] or null
   int n, L, step, n_cls, ncp;
+  unsigned long long* dbg;               // TT_DEC_DEBUG=1 (development): role cycle counters of CTA 0
 };
 
 struct alignas(16) Ctl {
   uint64_t full[kMaxStages], empty[kMaxStages];
-  uint64_t a_full;
+  uint64_t a_full, vec_full;
   uint64_t md[2];
   uint32_t tmem_base;
 };
@@ -69,7 +70,8 @@ struct Cfg {
   static constexpr int KB = D / 64;
   static constexpr int kStages = MODE == MODE_B ? 5 : 6;
   static constexpr int kVec = MODE == MODE_B ? 6 * D + MLP + 128 : 4 * D;
-  static constexpr int kSmem = KB * kUnit + (MODE == MODE_B ? 2 * kUnit : 0) + kStages * kUnit + kVec * 4 + static_cast<int>(sizeof(Ctl)) + 1024;
+  static constexpr int kXch = MODE == MODE_B ? 0 : 2 * 128 * 2 * 4;   // statistics exchange of the row-owner halves (MODE_B: inside sH)
+  static constexpr int kSmem = KB * kUnit + (MODE == MODE_B ? 2 * kUnit : 0) + kStages * kUnit + kVec * 4 + static_cast<int>(sizeof(Ctl)) + kXch + 1024;
   static_assert(D % 64 == 0 && D + 128 <= kTmemCols && MLP % 128 == 0, "decoder width");
   static_assert(kSmem <= 227 * 1024, "shared memory budget");
 };
@@ -90,44 +92,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_dec_dense(const __grid_constant
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
+  const long long t_entry = (p.dbg != nullptr && blockIdx.x == 0) ? clock64() : 0;
 
-  // per-column vectors -> smem (broadcast reads in the row loops)
-  if constexpr (MODE == MODE_B) {
-    for (int i = threadIdx.x; i < D; i += kThreads) {
-      vec[i] = p.b0[i]; vec[D + i] = p.lnA_g[i]; vec[2 * D + i] = p.lnA_b[i];
-      vec[3 * D + MLP + i] = p.b2[i]; vec[4 * D + MLP + i] = p.lnF_g[i]; vec[5 * D + MLP + i] = p.lnF_b[i];
-    }
-    for (int i = threadIdx.x; i < MLP; i += kThreads) vec[3 * D + i] = p.b1[i];
-    for (int i = threadIdx.x; i < 128; i += kThreads) vec[6 * D + MLP + i] = i < p.ncp ? p.bh[i] : 0.f;
-  } else {
-    for (int i = threadIdx.x; i < D; i += kThreads) {
-      vec[i] = p.b0[i] + p.posq_row[i]; vec[D + i] = p.lnA_g[i]; vec[2 * D + i] = p.lnA_b[i]; vec[3 * D + i] = p.b1[i];
-    }
-  }
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&p.tm_in);
     ptx::prefetch_tmap(&p.tm_w0);
     ptx::prefetch_tmap(&p.tm_w1);
     for (int s = 0; s < kStages; ++s) { ptx::mbar_init(&ctl->full[s], 1); ptx::mbar_init(&ctl->empty[s], 1); }
     ptx::mbar_init(&ctl->a_full, 1);
+    ptx::mbar_init(&ctl->vec_full, 1);
     ptx::mbar_init(&ctl->md[0], 1);
     ptx::mbar_init(&ctl->md[1], 1);
     ptx::fence_barrier_init();
+    // per-column vectors (biases, LayerNorm weights: packed in smem order at init) -> smem with ONE bulk copy that
+    // runs under the rest of the prologue; the row owners wait for it before their first phase.  (Per-thread staging
+    // loops took 12 000 cycles of a 100 000-cycle kernel.)
+    ptx::mbar_arrive_expect_tx(&ctl->vec_full, C::kVec * 4);
+    ptx::bulk_load(vec, p.vec_src, C::kVec * 4, &ctl->vec_full);
   }
   if (warp == 1) ptx::tmem_alloc(&ctl->tmem_base, kTmemCols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, ctl->tmem_base, 0);
+  if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[5] = clock64() - t_entry;   // prologue
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    const bool pdbg = p.dbg != nullptr && blockIdx.x == 0;
+    long long p_wait = 0;
+    const long long p_start = pdbg ? clock64() : 0;
     auto load = [&](const CUtensorMap* tm, int n_base, int k_base, int N, int K, int box_rows) {
       for (int kb = 0; kb < K / 64; ++kb)
         for (int n0 = 0; n0 < N; n0 += 128) {
-          ptx::mbar_wait(&ctl->empty[stage], phase ^ 1); __syncwarp();
+          { const long long t0 = pdbg ? clock64() : 0; ptx::mbar_wait(&ctl->empty[stage], phase ^ 1); __syncwarp(); p_wait += pdbg ? clock64() - t0 : 0; }
           ptx::mbar_arrive_expect_tx_e(&ctl->full[stage], static_cast<uint32_t>(box_rows) * 128u);
           ptx::tma_load_2d_e(ring + stage * kUnit, tm, &ctl->full[stage], k_base + kb * 64, n_base + n0);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -146,16 +146,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_dec_dense(const __grid_constant
       }
       load(&p.tm_wh, 0, 0, p.ncp, D, p.ncp < 128 ? p.ncp : 128);
     }
+    if (pdbg && lane == 0) { p.dbg[3] = p_wait; p.dbg[4] = clock64() - p_start; }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------- MMA issuer
     int stage = 0;
     uint32_t phase = 0, cnt = 0;
+    const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+    long long w_full = 0, w_bar = 0;
+    const long long t_start = dbg ? clock64() : 0;
     // acc[:, dcol + [0, N)) (+)= A[128 x K] * W[N x K]^T, units in the producer's order (k-block outer, 128-row chunk inner)
     auto gemm = [&](uint32_t a_addr0, int N, int K, uint32_t dcol, bool acc) {
       for (int kb = 0; kb < K / 64; ++kb)
         for (int n0 = 0; n0 < N; n0 += 128) {
           const int nn = N - n0 < 128 ? N - n0 : 128;
-          ptx::mbar_wait(&ctl->full[stage], phase); __syncwarp();
+          { const long long t0 = dbg ? clock64() : 0; ptx::mbar_wait(&ctl->full[stage], phase); __syncwarp(); w_full += dbg ? clock64() - t0 : 0; }
           ptx::tc_fence_after();
           const uint32_t b_addr = ptx::smem_u32(ring + stage * kUnit);
           const uint32_t idesc = ptx::make_idesc_bf16(128, nn);
@@ -168,7 +172,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_dec_dense(const __grid_constant
         }
     };
     auto commit_md = [&]() { ptx::mma_commit_e(&ctl->md[cnt & 1]); ++cnt; };
-    auto rows_done = [&]() { ptx::tc_fence_before(); ptx::named_bar_sync<1, 160>(); ptx::tc_fence_after(); };
+    auto rows_done = [&]() {
+      const long long t0 = dbg ? clock64() : 0;
+      ptx::tc_fence_before(); ptx::named_bar_sync<1, 32 + kRowThreads>(); ptx::tc_fence_after();
+      w_bar += dbg ? clock64() - t0 : 0;
+    };
     const uint32_t a_addr = ptx::smem_u32(sA), h_addr = ptx::smem_u32(sH);
     ptx::mbar_wait(&ctl->a_full, 0); __syncwarp();
     ptx::tc_fence_after();
@@ -194,16 +202,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_dec_dense(const __grid_constant
       gemm(a_addr, p.ncp, D, D, false); // head
       commit_md();
     }
+    if (dbg && lane == 0) { p.dbg[0] = w_full; p.dbg[1] = w_bar; p.dbg[2] = clock64() - t_start; }
   } else {
-    // ------------------------------------------------------------------- row owners (thread = crop)
+    // ------------------------------------------------- row owners (thread = crop; two warps per TMEM lane quadrant)
+    // Warps 2..5 take the lower half of a phase's columns, warps 6..9 the upper half of the same rows: LayerNorm's
+    // (sum, sum of squares) and the head's argmax are combined through a small smem exchange.
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const long long m = static_cast<long long>(tile) * 128 + r;
     const bool valid = m < p.n;
     const uint32_t tl = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t ecnt = 0;
     auto wait_md = [&]() { ptx::mbar_wait(&ctl->md[ecnt & 1], (ecnt >> 1) & 1); ++ecnt; ptx::tc_fence_after(); };
-    auto rows_done = [&]() { ptx::fence_proxy_async(); ptx::tc_fence_before(); ptx::named_bar_sync<1, 160>(); };
+    auto rows_done = [&]() { ptx::fence_proxy_async(); ptx::tc_fence_before(); ptx::named_bar_sync<1, 32 + kRowThreads>(); };
+    float* const xch = reinterpret_cast<float*>(MODE == MODE_B ? sH : reinterpret_cast<uint8_t*>(ctl + 1));   // [2][128][2] floats
+    // this thread's 32-column blocks [b0, b1) of TMEM columns tbase + blk * 32, the next block's load in flight while
+    // the current one is processed
+    auto for_blocks = [&](uint32_t tbase, int b0, int b1, auto&& f) {
+      uint32_t ra[32], rb[32];
+      if (b0 < b1) ptx::tmem_ld<32>(tbase + b0 * 32, ra);
+#pragma unroll 1
+      for (int blk = b0; blk < b1; blk += 2) {
+        ptx::tmem_ld_wait(ra);
+        if (blk + 1 < b1) ptx::tmem_ld<32>(tbase + (blk + 1) * 32, rb);
+        f(blk, ra);
+        if (blk + 1 < b1) {
+          ptx::tmem_ld_wait(rb);
+          if (blk + 2 < b1) ptx::tmem_ld<32>(tbase + (blk + 2) * 32, ra);
+          f(blk + 1, rb);
+        }
+      }
+    };
     // 32 bf16 columns [col0, col0 + 32) of this thread's row into a K-major SWIZZLE_128B operand buffer
     auto store_row32 = [&](uint8_t* base, int col0, const float (&y)[32]) {
       const uint32_t rowaddr = ptx::smem_u32(base) + (col0 >> 6) * kUnit + r * 128;
@@ -216,59 +246,60 @@ __global__ void __launch_bounds__(kThreads, 1) k_dec_dense(const __grid_constant
         ptx::sts128(rowaddr + (((j0 + jj) ^ (r & 7)) << 4), o);
       }
     };
-    // LayerNorm of the row held in TMEM columns [0, D) (+ bias vector `add`, may be null) -> bf16 -> sA
-    // (add / g / b are float offsets into `vec`; add < 0: none)
     const uint32_t vec_s = ptx::smem_u32(vec);
+    ptx::mbar_wait(&ctl->vec_full, 0);
+    constexpr int kDB = D / 32;                    // 32-column blocks of a row
+    const int db0 = half * (kDB / 2), db1 = db0 + kDB / 2;
+    // row statistics from the two halves' partial sums -> (mean, rstd)
+    auto combine_stats = [&](float s1, float s2, float& mean, float& rstd) {
+      xch[(half * 128 + r) * 2] = s1;
+      xch[(half * 128 + r) * 2 + 1] = s2;
+      ptx::named_bar_sync<2, kRowThreads>();
+      s1 += xch[((half ^ 1) * 128 + r) * 2];
+      s2 += xch[((half ^ 1) * 128 + r) * 2 + 1];
+      mean = s1 * (1.f / D);
+      rstd = rsqrtf(fmaxf(s2 * (1.f / D) - mean * mean, 0.f) + kEps);
+    };
+    // LayerNorm of the row held in TMEM columns [0, D) (+ bias vector `add`) -> bf16 -> sA  (add / g / b: float offsets
+    // into `vec`; add < 0: none)
     auto layernorm_to_sA = [&](int add, int g, int b, float mean, float rstd) {
-#pragma unroll 1
-      for (int blk = 0; blk < D / 32; ++blk) {
-        uint32_t raw[32];
-        ptx::tmem_ld<32>(tl + blk * 32, raw);
+      for_blocks(tl, db0, db1, [&](int blk, uint32_t (&raw)[32]) {
         float y[32], gv[32], bv[32];
         if (add >= 0) lds_f32x32(vec_s + (add + blk * 32) * 4, y);
         lds_f32x32(vec_s + (g + blk * 32) * 4, gv);
         lds_f32x32(vec_s + (b + blk * 32) * 4, bv);
-        ptx::tmem_ld_wait(raw);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float x = __uint_as_float(raw[j]) + (add >= 0 ? y[j] : 0.f);
           y[j] = (x - mean) * rstd * gv[j] + bv[j];
         }
         store_row32(sA, blk * 32, y);
-      }
+      });
     };
     float* const tcol = p.t_scratch + static_cast<size_t>(tile) * D * 128 + r;
 
     if constexpr (MODE == MODE_A2) {
       wait_md();
       float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-      for (int blk = 0; blk < D / 32; ++blk) {
-        uint32_t raw[32];
-        ptx::tmem_ld<32>(tl + blk * 32, raw);
+      for_blocks(tl, db0, db1, [&](int blk, uint32_t (&raw)[32]) {
         float av[32];
         lds_f32x32(vec_s + blk * 32 * 4, av);
-        ptx::tmem_ld_wait(raw);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float x = __uint_as_float(raw[j]) + av[j];   // + sa.out bias + pos_queries[step]
           sum += x; sq += x * x;
           tcol[static_cast<size_t>(blk * 32 + j) * 128] = x;            // lanes = consecutive crops: coalesced
         }
-      }
-      const float mean = sum * (1.f / D);
-      const float rstd = rsqrtf(fmaxf(sq * (1.f / D) - mean * mean, 0.f) + kEps);
+      });
+      float mean, rstd;
+      combine_stats(sum, sq, mean, rstd);
       layernorm_to_sA(0, D, 2 * D, mean, rstd);
       rows_done();
       wait_md();
       __nv_bfloat16* qrow = p.q_out + m * D;
-#pragma unroll 1
-      for (int blk = 0; blk < D / 32; ++blk) {
-        uint32_t raw[32];
-        ptx::tmem_ld<32>(tl + blk * 32, raw);
+      for_blocks(tl, db0, db1, [&](int blk, uint32_t (&raw)[32]) {
         float bq[32];
         lds_f32x32(vec_s + (3 * D + blk * 32) * 4, bq);
-        ptx::tmem_ld_wait(raw);
         if (valid) {
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
@@ -280,37 +311,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_dec_dense(const __grid_constant
             *reinterpret_cast<uint4*>(qrow + blk * 32 + 8 * jj) = o;
           }
         }
-      }
+      });
     } else {
       // ---- t = t_in + ca.out(ab2) + bias: into TMEM as fp32, LN2 -> sA
       float tin[2][32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) tin[0][j] = tcol[static_cast<size_t>(j) * 128];
+      for (int j = 0; j < 32; ++j) tin[0][j] = tcol[static_cast<size_t>(db0 * 32 + j) * 128];
       wait_md();
       float sum = 0.f, sq = 0.f;
-#pragma unroll
-      for (int blk = 0; blk < D / 32; ++blk) {
-        if (blk + 1 < D / 32) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) tin[(blk + 1) & 1][j] = tcol[static_cast<size_t>((blk + 1) * 32 + j) * 128];
-        }
-        uint32_t raw[32];
-        ptx::tmem_ld<32>(tl + blk * 32, raw);
-        float av[32];
-        lds_f32x32(vec_s + blk * 32 * 4, av);
-        ptx::tmem_ld_wait(raw);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float x = __uint_as_float(raw[j]) + av[j] + tin[blk & 1][j];
-          sum += x; sq += x * x;
-          raw[j] = __float_as_uint(x);
-        }
-        ptx::tmem_st32(tl + blk * 32, raw);
-      }
-      ptx::tmem_st_wait();
       {
-        const float mean = sum * (1.f / D);
-        const float rstd = rsqrtf(fmaxf(sq * (1.f / D) - mean * mean, 0.f) + kEps);
+        uint32_t raw[32];
+#pragma unroll
+        for (int i = 0; i < kDB / 2; ++i) {
+          const int blk = db0 + i;
+          ptx::tmem_ld<32>(tl + blk * 32, raw);
+          if (i + 1 < kDB / 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tin[(i + 1) & 1][j] = tcol[static_cast<size_t>((blk + 1) * 32 + j) * 128];
+          }
+          float av[32];
+          lds_f32x32(vec_s + blk * 32 * 4, av);
+          ptx::tmem_ld_wait(raw);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(raw[j]) + av[j] + tin[i & 1][j];
+            sum += x; sq += x * x;
+            raw[j] = __float_as_uint(x);
+          }
+          ptx::tmem_st32(tl + blk * 32, raw);
+          ptx::tmem_st_wait();
+        }
+      }
+      {
+        float mean, rstd;
+        combine_stats(sum, sq, mean, rstd);
         layernorm_to_sA(-1, D, 2 * D, mean, rstd);
       }
       rows_done();
@@ -318,56 +352,46 @@ __global__ void __launch_bounds__(kThreads, 1) k_dec_dense(const __grid_constant
 #pragma unroll 1
       for (int c = 0; c < NC; ++c) {
         wait_md();
-#pragma unroll 1
-        for (int b4 = 0; b4 < 4; ++b4) {
-          uint32_t raw[32];
-          ptx::tmem_ld<32>(tl + D + b4 * 32, raw);
+        for_blocks(tl + D, half * 2, half * 2 + 2, [&](int b4, uint32_t (&raw)[32]) {
           float y[32], b1[32];
           lds_f32x32(vec_s + (3 * D + c * 128 + b4 * 32) * 4, b1);
-          ptx::tmem_ld_wait(raw);
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             const uint64_t v = gelu_fast2(add2(pk2u(raw[j], raw[j + 1]), pk2(b1[j], b1[j + 1])));
             upk2(v, y[j], y[j + 1]);
           }
           store_row32(sH, b4 * 32, y);
-        }
+        });
         rows_done();
       }
       // ---- final norm of t (+ l2 bias) -> sA
       wait_md();
       {
         float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-        for (int blk = 0; blk < D / 32; ++blk) {
-          uint32_t raw[32];
-          ptx::tmem_ld<32>(tl + blk * 32, raw);
+        for_blocks(tl, db0, db1, [&](int blk, uint32_t (&raw)[32]) {
           float b2[32];
           lds_f32x32(vec_s + (3 * D + MLP + blk * 32) * 4, b2);
-          ptx::tmem_ld_wait(raw);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float x = __uint_as_float(raw[j]) + b2[j];
             s1 += x; s2 += x * x;
           }
-        }
-        const float mean = s1 * (1.f / D);
-        const float rstd = rsqrtf(fmaxf(s2 * (1.f / D) - mean * mean, 0.f) + kEps);
+        });
+        float mean, rstd;
+        combine_stats(s1, s2, mean, rstd);
         layernorm_to_sA(3 * D + MLP, 4 * D + MLP, 5 * D + MLP, mean, rstd);
       }
       rows_done();
-      // ---- head: logits row + greedy token
+      // ---- head: logits row + greedy token (the halves' maxima meet in smem; the lower half holds the lower classes)
       wait_md();
       {
         float* lrow = p.logits + (m * p.L + p.step) * p.ncp;
         float best = -INFINITY;
         int bi = 0;
-        for (int blk = 0; blk < p.ncp / 32; ++blk) {
-          uint32_t raw[32];
-          ptx::tmem_ld<32>(tl + D + blk * 32, raw);
+        const int nb = p.ncp / 32, hb0 = half ? (nb + 1) / 2 : 0, hb1 = half ? nb : (nb + 1) / 2;
+        for_blocks(tl + D, hb0, hb1, [&](int blk, uint32_t (&raw)[32]) {
           float l[32];
           lds_f32x32(vec_s + (6 * D + MLP + blk * 32) * 4, l);
-          ptx::tmem_ld_wait(raw);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             l[j] += __uint_as_float(raw[j]);
@@ -378,14 +402,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_dec_dense(const __grid_constant
             for (int jj = 0; jj < 8; ++jj)
               *reinterpret_cast<float4*>(lrow + blk * 32 + 4 * jj) = make_float4(l[4 * jj], l[4 * jj + 1], l[4 * jj + 2], l[4 * jj + 3]);
           }
+        });
+        if (half == 1) { xch[r * 2] = best; xch[r * 2 + 1] = __int_as_float(bi); }
+        ptx::named_bar_sync<2, kRowThreads>();
+        if (half == 0) {
+          const float ob = xch[r * 2];
+          if (ob > best) { best = ob; bi = __float_as_int(xch[r * 2 + 1]); }
+          if (valid && p.step + 1 < p.L)
+            p.tokens[m * p.L + p.step + 1] = p.forced ? p.forced[m * (p.L - 1) + p.step] : bi;
         }
-        if (valid && p.step + 1 < p.L)
-          p.tokens[m * p.L + p.step + 1] = p.forced ? p.forced[m * (p.L - 1) + p.step] : bi;
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[6] = clock64() - t_entry;   // entry -> all roles done
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kTmemCols);
@@ -432,8 +463,23 @@ cudaError_t launch_dense(const DenseParams& p, cudaStream_t s) {
   at[0].val.priority = dense_priority();
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  TT_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_dec_dense<D, MLP, MODE>, p));
+  static const bool dbg_env = std::getenv("TT_DEC_DEBUG") && std::atoi(std::getenv("TT_DEC_DEBUG")) != 0;
+  static unsigned long long* dbg_buf = nullptr;
+  DenseParams pp = p;
+  if (dbg_env) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 8 * sizeof(unsigned long long));
+    cudaMemsetAsync(dbg_buf, 0, 8 * sizeof(unsigned long long), s);
+    pp.dbg = dbg_buf;
+  }
+  TT_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_dec_dense<D, MLP, MODE>, pp));
   TT_LAUNCH_CHECK();
+  if (dbg_env && p.step == 13) {
+    unsigned long long h[8];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    std::fprintf(stderr, "[dec dbg] mode %d n %d: mma wait-full %llu wait-rows %llu total %llu | producer wait-empty %llu total %llu | prologue %llu entry-to-done %llu\n",
+                 MODE, p.n, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+  }
   return cudaSuccess;
 }
 
@@ -458,6 +504,41 @@ bool dec_dense_init(DecDenseWeights* w, int D, int mlp, int n_cls, int ncp, int 
   return true;
 }
 
+namespace {
+__global__ void k_dec_pack(DecDenseWeights w, float* vec_b, float* vec_a2) {
+  const int D = w.D, MLP = w.mlp;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < D) {
+    vec_b[i] = w.bco[i]; vec_b[D + i] = w.n2_g[i]; vec_b[2 * D + i] = w.n2_b[i];
+    vec_b[3 * D + MLP + i] = w.b2[i]; vec_b[4 * D + MLP + i] = w.nf_g[i]; vec_b[5 * D + MLP + i] = w.nf_b[i];
+    for (int st = 0; st < w.L; ++st) {
+      float* a = vec_a2 + static_cast<size_t>(st) * 4 * D;
+      a[i] = w.bo[i] + w.posq[static_cast<size_t>(st) * D + i];
+      a[D + i] = w.n1_g[i]; a[2 * D + i] = w.n1_b[i]; a[3 * D + i] = w.bq[i];
+    }
+  }
+  if (i < MLP) vec_b[3 * D + i] = w.b1[i];
+  if (i < 128) vec_b[6 * D + MLP + i] = i < w.ncp ? w.bh[i] : 0.f;
+}
+}  // namespace
+
+cudaError_t dec_dense_pack(DecDenseWeights* w, cudaStream_t s) {
+  if (!w->ready) return cudaSuccess;
+  dec_dense_free(w);
+  TT_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w->vec_b), sizeof(float) * (6 * w->D + w->mlp + 128)));
+  TT_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w->vec_a2), sizeof(float) * w->L * 4 * w->D));
+  const int n = std::max(w->mlp, std::max(w->D, 128));
+  k_dec_pack<<<(n + 255) / 256, 256, 0, s>>>(*w, w->vec_b, w->vec_a2);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+void dec_dense_free(DecDenseWeights* w) {
+  if (w->vec_b) cudaFree(w->vec_b);
+  if (w->vec_a2) cudaFree(w->vec_a2);
+  w->vec_b = w->vec_a2 = nullptr;
+}
+
 cudaError_t dec_dense_a2(const DecDenseWeights& w, const __nv_bfloat16* ab, int n, int step, float* t_scratch,
                          __nv_bfloat16* q_out, cudaStream_t s) {
   if (n <= 0) return cudaSuccess;
@@ -465,9 +546,7 @@ cudaError_t dec_dense_a2(const DecDenseWeights& w, const __nv_bfloat16* ab, int 
   DenseParams p{};
   if (!make_in_map(&p.tm_in, ab, n, w.D)) return cudaErrorInvalidValue;
   p.tm_w0 = w.tm_wo; p.tm_w1 = w.tm_wq; p.tm_w2 = w.tm_wq; p.tm_wh = w.tm_wq;
-  p.b0 = w.bo; p.b1 = w.bq;
-  p.lnA_g = w.n1_g; p.lnA_b = w.n1_b;
-  p.posq_row = w.posq + static_cast<size_t>(step) * w.D;
+  p.vec_src = w.vec_a2 + static_cast<size_t>(step) * 4 * w.D;
   p.t_scratch = t_scratch; p.q_out = q_out;
   p.n = n; p.L = w.L; p.step = step; p.n_cls = w.n_cls; p.ncp = w.ncp;
   if (w.D == 384) return launch_dense<384, 1536, MODE_A2>(p, s);
@@ -481,8 +560,7 @@ cudaError_t dec_dense_b(const DecDenseWeights& w, const __nv_bfloat16* ab2, int 
   DenseParams p{};
   if (!make_in_map(&p.tm_in, ab2, n, w.D)) return cudaErrorInvalidValue;
   p.tm_w0 = w.tm_wco; p.tm_w1 = w.tm_w1; p.tm_w2 = w.tm_w2; p.tm_wh = w.tm_wh;
-  p.b0 = w.bco; p.b1 = w.b1; p.b2 = w.b2; p.bh = w.bh;
-  p.lnA_g = w.n2_g; p.lnA_b = w.n2_b; p.lnF_g = w.nf_g; p.lnF_b = w.nf_b;
+  p.vec_src = w.vec_b;
   p.t_scratch = const_cast<float*>(t_scratch);
   p.logits = logits; p.tokens = tokens; p.forced = forced;
   p.n = n; p.L = w.L; p.step = step; p.n_cls = w.n_cls; p.ncp = w.ncp;

@@ -24,6 +24,11 @@ struct DecDenseWeights {
   const float *bo = nullptr, *bq = nullptr, *bco = nullptr, *b1 = nullptr, *b2 = nullptr, *bh = nullptr;
   const float *n1_g = nullptr, *n1_b = nullptr, *n2_g = nullptr, *n2_b = nullptr, *nf_g = nullptr, *nf_b = nullptr;
   const float* posq = nullptr;   // [L][D]
+  // the kernels' per-column vectors packed in smem order (device memory owned by this struct's user, see dec_dense_pack):
+  //   vec_b  [6 D + mlp + 128]: bco | n2_g | n2_b | b1 | b2 | nf_g | nf_b | bh (zero padded to 128)
+  //   vec_a2 [L][4 D]         : bo + posq[step] | n1_g | n1_b | bq
+  float* vec_b = nullptr;
+  float* vec_a2 = nullptr;
   int D = 0, mlp = 0, n_cls = 0, ncp = 0, L = 0;
   bool ready = false;
 };
@@ -33,6 +38,10 @@ bool dec_dense_init(DecDenseWeights* w, int D, int mlp, int n_cls, int ncp, int 
                     const __nv_bfloat16* wq, const __nv_bfloat16* wco, const __nv_bfloat16* w1, const __nv_bfloat16* w2,
                     const __nv_bfloat16* wh);
 bool dec_dense_supported(int D, int mlp, int ncp);
+// After the bias / LayerNorm / posq pointers are set: allocates and fills vec_b / vec_a2 on the current device
+// (dec_dense_free releases them).
+cudaError_t dec_dense_pack(DecDenseWeights* w, cudaStream_t s);
+void dec_dense_free(DecDenseWeights* w);
 
 // fp32 scratch the two kernels hand the residual row through: [ceil(n/128)][D][128] (column-major per 128-crop tile).
 size_t dec_dense_scratch_floats(int n, int D);

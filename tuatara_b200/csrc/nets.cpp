@@ -437,6 +437,7 @@ DeviceWeights::~DeviceWeights() {
   if (q_sa_table) cudaFree(q_sa_table);
   if (kv_table) cudaFree(kv_table);
   if (sc_table) cudaFree(sc_table);
+  dec_dense_free(&dd);
 }
 
 DeviceCtx::~DeviceCtx() {
@@ -529,6 +530,7 @@ cudaError_t DeviceCtx::init(const std::string& dir, std::shared_ptr<DeviceWeight
     dd.n1_g = wf.f32("dec.n1.g"); dd.n1_b = wf.f32("dec.n1.b"); dd.n2_g = wf.f32("dec.n2.g"); dd.n2_b = wf.f32("dec.n2.b");
     dd.nf_g = wf.f32("dec.norm.g"); dd.nf_b = wf.f32("dec.norm.b");
     dd.posq = wf.f32("posq");
+    RUN(dec_dense_pack(&dd, stream));
   }
   TT_CUDA_TRY(stream_sync(stream));
   return cudaSuccess;

@@ -6,6 +6,8 @@
 #include <cuda.h>
 #include <math.h>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
