@@ -358,8 +358,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // named barrier `id` over `threads` threads (a multiple of 32) of the CTA
+// (barrier.sync without .aligned: the participating warps arrive from different instructions -- the MMA issuer's and the
+// row owners' -- and a warp may still be re-converging from an mbarrier spin loop; __syncwarp first keeps it whole)
 template <int ID, int THREADS>
-__device__ __forceinline__ void named_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(THREADS) : "memory"); }
+__device__ __forceinline__ void named_bar_sync() {
+  __syncwarp();
+  asm volatile("barrier.sync %0, %1;" ::"n"(ID), "n"(THREADS) : "memory");
+}
 // Same, but names the destination registers of the outstanding load as in/out operands so the compiler
 // cannot schedule a read of them above the wait (the load completes asynchronously).
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
