@@ -183,10 +183,11 @@ TT_API int tt_rect_to_bbox(const float rect[5], float bbox_out[4]);
 TT_API int tt_linear_dev(const void* A, int lda, int M, int K, const void* W, int N, const float* bias, int act,
                   const void* residual, int res_f32, int ldr, void* out, int out_f32, int ldc, int BN, int resident,
                   void* stream);
-/* Kernel test of the fused LayerNorm pair the PARSeq encoder runs (x += A W1^T + b1; y = act(Linear(LN(x)))):
- * X fp32 [M][D] in/out, XB bf16 [M][D] out, stats fp32 [M][8] scratch, W2f = W2 * gamma (bf16 [N2][D]),
- * c0[n] = b2[n] + beta . W2[n], c1[n] = sum_k W2f[n][k]; out bf16 [M][N2].  All device pointers. */
-TT_API int tt_linear_ln_pair_dev(const void* A, int M, int K1, const void* W1, const float* b1, int D, float* X, void* XB,
+/* Kernel test of the fused LayerNorm pair the PARSeq encoder runs (x += A W1^T + b1; y = act(Linear(LN(x)))).  The fp32
+ * residual stream x is kept split: x_hi = bf16(x), x_lo = bf16(x - x_hi), both bf16 [M][D], updated in place (x_hi is
+ * the second GEMM's A operand).  stats fp32 [M][8] scratch, W2f = W2 * gamma (bf16 [N2][D]), c0[n] = b2[n] + beta . W2[n],
+ * c1[n] = sum_k W2f[n][k]; out bf16 [M][N2].  All device pointers. */
+TT_API int tt_linear_ln_pair_dev(const void* A, int M, int K1, const void* W1, const float* b1, int D, void* x_hi, void* x_lo,
                           float* stats, const void* W2f, const float* c0, const float* c1, int N2, int act, float eps,
                           void* out, void* stream);
 /* NHWC bf16 stride-1 "same" convolution as implicit GEMM; src1 may be NULL (else channel concat).

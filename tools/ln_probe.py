@@ -23,13 +23,14 @@ def main():
     W1 = (torch.randn(D, K1, generator=g) * 0.05).to(torch.bfloat16).cuda()
     b1 = torch.zeros(D).cuda()
     X = torch.randn(M, D, generator=g).cuda()
-    XB = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
+    XH = X.to(torch.bfloat16)
+    XL = (X - XH.float()).to(torch.bfloat16)
     stats = torch.zeros(M, 8, device="cuda")
     W2f = (torch.randn(N2, D, generator=g) * 0.05).to(torch.bfloat16).cuda()
     c0, c1 = torch.zeros(N2).cuda(), W2f.float().sum(1)
     out = torch.empty(M, N2, dtype=torch.bfloat16, device="cuda")
     for _ in range(reps):
-        check(lib.tt_linear_ln_pair_dev(A.data_ptr(), M, K1, W1.data_ptr(), b1.data_ptr(), D, X.data_ptr(), XB.data_ptr(),
+        check(lib.tt_linear_ln_pair_dev(A.data_ptr(), M, K1, W1.data_ptr(), b1.data_ptr(), D, XH.data_ptr(), XL.data_ptr(),
                                         stats.data_ptr(), W2f.data_ptr(), c0.data_ptr(), c1.data_ptr(), N2, act, 1e-6,
                                         out.data_ptr(), None), "tt_linear_ln_pair_dev")
     torch.cuda.synchronize()

@@ -316,24 +316,25 @@ int tt_linear_dev(const void* A, int lda, int M, int K, const void* W, int N, co
   });
 }
 
-int tt_linear_ln_pair_dev(const void* A, int M, int K1, const void* W1, const float* b1, int D, float* X, void* XB,
+int tt_linear_ln_pair_dev(const void* A, int M, int K1, const void* W1, const float* b1, int D, void* x_hi, void* x_lo,
                           float* stats, const void* W2f, const float* c0, const float* c1, int N2, int act, float eps,
                           void* out, void* stream) {
   return guarded([&]() -> int {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int parts = 0;
-    {  // producer: X += A W1^T + b1, plus bf16(X) and the rows' partial (sum, sum of squares)
+    {  // producer: x += A W1^T + b1 on the split (hi, lo) stream, plus the rows' partial (sum, sum of squares)
       LinearProblem l;
       l.A = static_cast<const __nv_bfloat16*>(A); l.lda = K1; l.M = M; l.K = K1;
       l.W = static_cast<const __nv_bfloat16*>(W1); l.N = D;
       Epilogue e;
-      e.bias = b1; e.residual = X; e.res_type = RES_F32; e.ldr = D; e.out = X; e.out_type = OUT_F32; e.ldc = D;
-      e.ln_xb_out = static_cast<__nv_bfloat16*>(XB); e.ldxb = D; e.ln_stats_out = stats; e.ln_parts_out = &parts;
+      e.bias = b1; e.residual = x_hi; e.residual_lo = x_lo; e.res_type = RES_SPLIT; e.ldr = D;
+      e.out = x_hi; e.out_lo = x_lo; e.out_type = OUT_SPLIT; e.ldc = D;
+      e.ln_stats_out = stats; e.ln_parts_out = &parts;
       if (linear_forward(l, e, s) != cudaSuccess) return 1;
     }
-    {  // consumer: out = act(Linear(LN(X))) from bf16(X), the folded weights and the statistics
+    {  // consumer: out = act(Linear(LN(x))) from hi = bf16(x), the folded weights and the statistics
       LinearProblem l;
-      l.A = static_cast<const __nv_bfloat16*>(XB); l.lda = D; l.M = M; l.K = D;
+      l.A = static_cast<const __nv_bfloat16*>(x_hi); l.lda = D; l.M = M; l.K = D;
       l.W = static_cast<const __nv_bfloat16*>(W2f); l.N = N2;
       Epilogue e;
       e.bias = c0; e.act = act; e.out = out; e.out_type = OUT_BF16; e.ldc = N2;

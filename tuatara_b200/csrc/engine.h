@@ -71,6 +71,7 @@ struct DeviceWeights {
   ParseqDims pd;
   float* q_sa_table = nullptr;  // [L][D] fp32: self-attn queries of the 26 positions (crop independent)
   __nv_bfloat16* kv_table = nullptr;  // [L][n_tok][2D] bf16: content-stream K|V of every (position, token) pair
+  __nv_bfloat16* pos_split = nullptr;  // [2][128][D] bf16: pos_embed as a (hi, lo) pair, the patch embedding's split residual
   float* sc_table = nullptr;    // [L][L][n_tok][dec_heads] fp32: AR self-attention scores as a lookup (nn_kernels.cuh)
   DecDenseWeights dd;           // tensor maps + vectors of the fused decoder kernels (dec_fused.cu)
   ~DeviceWeights();

@@ -54,14 +54,14 @@ constexpr int kHaloPixels = kHaloRows * kHaloPitch;           // x 128 B (64 cha
 constexpr int kHaloResidentMax = 82 * 1024;                  // weights that leave room for 3 halo stages in one CTA
 constexpr int kResSlots = 4;
 constexpr int kResSlotBytes = 128 * 128;    // fp32 chunk [128 rows][32 cols]
-constexpr int kLnCopyBytes = 4 * 2 * 2048;  // LayerNorm-statistics producer: two 2 KB bf16 store tiles per epilogue warp
 
 struct KParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
   CUtensorMap tmR, tmC;  // TMA epilogue: fp32 residual (load) and output (store), box {32 cols, 128 rows}
   CUtensorMap tmP;       // fused 2x2 max-pool: the pooled output, box {32 ch, TW/2, 16/TW, 1}, SWIZZLE_64B
-  CUtensorMap tmCb;      // LayerNorm-statistics producer: bf16 copy of the output, box {32 cols, 32 rows}, SWIZZLE_64B
+  CUtensorMap tmR2, tmC2;  // split residual stream (RES_SPLIT / OUT_SPLIT): the lo tensors; tmR / tmC are then the hi tensors,
+                           // all four bf16 with box {32 cols, 128 rows}, SWIZZLE_64B
   int mode;  // 0 plain rows, 1 conv tiles
   int M, N, BN, BK;
   int kb_src[2];
@@ -168,10 +168,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
   uint8_t* sBres = smem;                                        // [num_kb][BN rows] when resident
   uint8_t* ring = smem + (resident ? num_kb * b_bytes : 0);
   uint8_t* res_ring = ring + p.stages * stage_bytes;            // TE only
-  uint8_t* ln_copy = res_ring + kResSlots * kSlot;               // TE && LN only
-  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(res_ring + (TE ? kResSlots * kSlot + (LN ? kLnCopyBytes : 0)
-                                                           : TS ? EW * kTsBufs * 2048 + (POOL ? EW * kTsBufs * 512 : 0) : 0));
-  (void)ln_copy;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(res_ring + (TE ? kResSlots * kSlot : TS ? EW * kTsBufs * 2048 + (POOL ? EW * kTsBufs * 512 : 0) : 0));
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -194,7 +191,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
     if constexpr (TE) {
       ptx::prefetch_tmap(&p.tmR);
       ptx::prefetch_tmap(&p.tmC);
-      if constexpr (LN) ptx::prefetch_tmap(&p.tmCb);
+      if constexpr (LN) { ptx::prefetch_tmap(&p.tmR2); ptx::prefetch_tmap(&p.tmC2); }
       for (int s = 0; s < kResSlots; ++s) {
         ptx::mbar_init(&ctl->res_full[s], 1);
         ptx::mbar_init(&ctl->res_empty[s], 1);
@@ -389,6 +386,8 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
           ptx::mbar_arrive_expect_tx_e(&ctl->res_full[slot], kResSlotBytes);
           // a pair's second tile may not exist, columns may end before the tile does: out-of-bounds parts arrive as zeros
           ptx::tma_load_2d_e(res_ring + slot * kSlot, &p.tmR, &ctl->res_full[slot], n0 + c * 32, rrow);
+          if constexpr (LN)   // split residual: hi tile [128 rows x 64 B] then lo tile, 8 KB each
+            ptx::tma_load_2d_e(res_ring + slot * kSlot + kResSlotBytes / 2, &p.tmR2, &ctl->res_full[slot], n0 + c * 32, rrow);
           if (++slot == kResSlots) { slot = 0; ph ^= 1; }
         }
       }
@@ -403,7 +402,10 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
         const int n0 = it.n_tile(p) * p.BN, m0 = m_tile * kBlockM;
         for (int c = 0; c < p.BN / 32; ++c) {
           ptx::mbar_wait(&ctl->chunk_done[slot], ph); __syncwarp();
-          if ((p.debug & 3) == 0) ptx::tma_store_2d_e(&p.tmC, res_ring + slot * kSlot, n0 + c * 32, m0);  // rows/cols past the tensor are clipped
+          if ((p.debug & 3) == 0) {
+            ptx::tma_store_2d_e(&p.tmC, res_ring + slot * kSlot, n0 + c * 32, m0);  // rows/cols past the tensor are clipped
+            if constexpr (LN) ptx::tma_store_2d_e(&p.tmC2, res_ring + slot * kSlot + kResSlotBytes / 2, n0 + c * 32, m0);
+          }
           ptx::bulk_commit_e();
           if (prev >= 0) {
             if (ptx::elect_one()) ptx::bulk_wait_read<1>();   // the previous chunk's store has finished reading its slot
@@ -520,9 +522,9 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
     (void)ln_s1n; (void)ln_s2n;
     const uint32_t c1_s = ptx::smem_u32(&ctl->c1[0][0]);
     (void)c1_s;
-    int te_slot = 0, ln_buf = 0;
+    int te_slot = 0;
     uint32_t te_ph = 0;
-    (void)te_slot; (void)te_ph; (void)ln_buf;
+    (void)te_slot; (void)te_ph;
     for (; it.valid(); it.next()) {
       const int n_tile = it.n_tile(p), m_tile = PAIR ? it.m_tile(p) * 2 + static_cast<int>(rank) : it.m_tile(p);
       const int n0 = n_tile * BN;
@@ -570,50 +572,49 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
           ptx::tmem_ld<32>(t_row + c * 32, raw);
           ptx::mbar_wait(&ctl->res_full[te_slot], te_ph);
           ptx::tmem_ld_wait(raw);
-          const uint32_t rowaddr = ring_s + te_slot * kSlot + r * 128;
           if (dbg != 2) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint32_t a = rowaddr + ((k ^ (r & 7)) << 4);
-              const uint4 u = ptx::lds128(a);
-              const uint4 b = ptx::lds128(bias_row + (c * 32 + 4 * k) * 4);
-              const uint64_t v0 = add2(add2(pk2u(raw[4 * k + 0], raw[4 * k + 1]), pk2u(b.x, b.y)), pk2u(u.x, u.y));
-              const uint64_t v1 = add2(add2(pk2u(raw[4 * k + 2], raw[4 * k + 3]), pk2u(b.z, b.w)), pk2u(u.z, u.w));
-              uint4 o;
-              upk2u(v0, o.x, o.y);
-              upk2u(v1, o.z, o.w);
-              ptx::sts128(a, o);
-              if constexpr (LN) {
-                ln_s1 = add2(ln_s1, add2(v0, v1));
-                ln_s2 = fma2(v0, v0, fma2(v1, v1, ln_s2));
-                raw[4 * k + 0] = o.x; raw[4 * k + 1] = o.y; raw[4 * k + 2] = o.z; raw[4 * k + 3] = o.w;   // keep x for the bf16 copy
-              }
-            }
             if constexpr (LN) {
-              // bf16 copy of the chunk, the way the TMA-store epilogue does it: this warp's 32 rows x 64 B go into a
-              // warp-private SWIZZLE_64B tile (two alternate) and one lane hands it to a TMA store.  (Per-thread global
-              // stores of 64-byte row pieces made proj 38 % slower, a 128-row tile per ring slot cost an operand stage.)
-              if (lane == 0) ptx::bulk_wait_read<1>();   // the store issued from this tile two chunks ago has read it
-              __syncwarp();
-              const uint32_t tile_s = ptx::smem_u32(ln_copy) + ((warp - kEpiWarp0) * 2 + ln_buf) * 2048;
-              const uint32_t brow = tile_s + lane * 64;
-              const int sw = (lane >> 1) & 3;
+              // split residual stream: this thread's row of the hi tile at r*64, of the lo tile 8 KB behind it, 16-byte
+              // units (8 bf16) XOR-swizzled by (r >> 1) & 3 (SWIZZLE_64B).  x = hi + lo + acc + bias in fp32; written back
+              // as hi' = bf16(x), lo' = bf16(x - hi') in place -- hi' is the next GEMM's A operand.
+              const uint32_t hrow = ring_s + te_slot * kSlot + r * 64;
+              const int sw = (r >> 1) & 3;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
+                const uint32_t a = hrow + ((j ^ sw) << 4);
+                const uint4 h = ptx::lds128(a), l = ptx::lds128(a + kResSlotBytes / 2);
+                const uint4 b0 = ptx::lds128(bias_row + (c * 32 + 8 * j) * 4), b1 = ptx::lds128(bias_row + (c * 32 + 8 * j + 4) * 4);
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+                const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t ho[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {   // two columns per 32-bit word: low half = even column
+                  const uint64_t res = add2(pk2u(hw[e] << 16, hw[e] & 0xffff0000u), pk2u(lw[e] << 16, lw[e] & 0xffff0000u));
+                  const uint64_t v = add2(add2(pk2u(raw[8 * j + 2 * e], raw[8 * j + 2 * e + 1]), pk2u(bw[2 * e], bw[2 * e + 1])), res);
+                  ln_s1 = add2(ln_s1, v);
+                  ln_s2 = fma2(v, v, ln_s2);
+                  float x0, x1;
+                  upk2(v, x0, x1);
+                  ho[e] = pack_bf16(x0, x1);
+                  lo[e] = pack_bf16(x0 - __uint_as_float(ho[e] << 16), x1 - __uint_as_float(ho[e] & 0xffff0000u));
+                }
+                ptx::sts128(a, make_uint4(ho[0], ho[1], ho[2], ho[3]));
+                ptx::sts128(a + kResSlotBytes / 2, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+              }
+            } else {
+              const uint32_t rowaddr = ring_s + te_slot * kSlot + r * 128;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t a = rowaddr + ((k ^ (r & 7)) << 4);
+                const uint4 u = ptx::lds128(a);
+                const uint4 b = ptx::lds128(bias_row + (c * 32 + 4 * k) * 4);
+                const uint64_t v0 = add2(add2(pk2u(raw[4 * k + 0], raw[4 * k + 1]), pk2u(b.x, b.y)), pk2u(u.x, u.y));
+                const uint64_t v1 = add2(add2(pk2u(raw[4 * k + 2], raw[4 * k + 3]), pk2u(b.z, b.w)), pk2u(u.z, u.w));
                 uint4 o;
-                o.x = pack_bf16(__uint_as_float(raw[8 * j + 0]), __uint_as_float(raw[8 * j + 1]));
-                o.y = pack_bf16(__uint_as_float(raw[8 * j + 2]), __uint_as_float(raw[8 * j + 3]));
-                o.z = pack_bf16(__uint_as_float(raw[8 * j + 4]), __uint_as_float(raw[8 * j + 5]));
-                o.w = pack_bf16(__uint_as_float(raw[8 * j + 6]), __uint_as_float(raw[8 * j + 7]));
-                ptx::sts128(brow + ((j ^ sw) << 4), o);
+                upk2u(v0, o.x, o.y);
+                upk2u(v1, o.z, o.w);
+                ptx::sts128(a, o);
               }
-              ptx::fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) {
-                if (dbg == 0) ptx::tma_store_2d_s(&p.tmCb, tile_s, n0 + c * 32, m_tile * kBlockM + q * 32);   // rows past M are clipped
-                ptx::bulk_commit();
-              }
-              ln_buf ^= 1;
             }
           }
           ptx::fence_proxy_async();
@@ -858,7 +859,7 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
       ++dbg_tiles;
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if constexpr (TS || (TE && LN)) { if (lane == 0) ptx::bulk_wait<0>(); }
+    if constexpr (TS) { if (lane == 0) ptx::bulk_wait<0>(); }
     if ((p.debug & 4) && blockIdx.x == 0 && lane == 0 && (warp == kEpiWarp0 || warp == kEpiWarp0 + 4)) {
       const int o = (warp == kEpiWarp0 + 4) * 3;
       p.dbg_out[5 + o] = dbg_e_wait; p.dbg_out[6 + o] = dbg_e_busy; p.dbg_out[7 + o] = dbg_tiles;
@@ -1086,9 +1087,13 @@ bool tma_epilogue_ok(const KParams& kp) {
   const Epilogue& e = kp.epi;
   // Only for launches that fill the GPU: small ones are latency bound and gain nothing from the extra two warps and the
   // 64 KB ring (TT_GEMM_TE=2 forces it everywhere: the regime of the round-1 hang, kept for the regression probe).
-  const bool want_stats = e.ln_stats_out != nullptr;   // the LayerNorm-statistics producer exists only as a TMA epilogue
-  if (te_env != 2 && !want_stats && kp.m_tiles_total < 2 * num_sms()) return false;
-  return (te_env != 0 || want_stats) && kp.mode == 0 && e.out_type == OUT_F32 && e.res_type == RES_F32 && e.act == ACT_NONE && kp.BN % 32 == 0 &&
+  if (e.out_type == OUT_SPLIT)   // the split residual stream (LayerNorm-statistics producer) exists only as a TMA epilogue
+    return kp.mode == 0 && e.res_type == RES_SPLIT && e.act == ACT_NONE && kp.BN % 32 == 0 && kp.N % 8 == 0 && e.ldc % 8 == 0 &&
+           e.ldr % 8 == 0 && (e.res_mod == 0 || e.res_mod % kBlockM == 0) && e.out_lo != nullptr && e.residual_lo != nullptr &&
+           reinterpret_cast<uintptr_t>(e.out) % 16 == 0 && reinterpret_cast<uintptr_t>(e.residual) % 16 == 0 &&
+           reinterpret_cast<uintptr_t>(e.out_lo) % 16 == 0 && reinterpret_cast<uintptr_t>(e.residual_lo) % 16 == 0;
+  if (te_env != 2 && kp.m_tiles_total < 2 * num_sms()) return false;
+  return te_env != 0 && kp.mode == 0 && e.out_type == OUT_F32 && e.res_type == RES_F32 && e.act == ACT_NONE && kp.BN % 32 == 0 &&
          kp.N % 4 == 0 && e.ldc % 4 == 0 && e.ldr % 4 == 0 && (e.res_mod == 0 || e.res_mod % kBlockM == 0) &&
          reinterpret_cast<uintptr_t>(e.out) % 16 == 0 && reinterpret_cast<uintptr_t>(e.residual) % 16 == 0;
 }
@@ -1119,8 +1124,8 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   }
   KernelFn fn;
   const bool ln_prod = kp.epi.ln_stats_out != nullptr, ln_cons = kp.epi.ln_stats_in != nullptr;
-  if (ln_prod && (!te || kp.epi.ln_xb_out == nullptr || kp.epi.ldxb % 8 != 0 || reinterpret_cast<uintptr_t>(kp.epi.ln_xb_out) % 16 != 0 || kp.num_n_tiles > 4)) {
-    set_error("gemm: LayerNorm statistics need the TMA epilogue (fp32 out + fp32 residual), a bf16 copy target and <= 4 N tiles");
+  if ((ln_prod || kp.epi.out_type == OUT_SPLIT) && (!te || !ln_prod || kp.epi.out_type != OUT_SPLIT || kp.num_n_tiles > 4)) {
+    set_error("gemm: the LayerNorm-statistics producer is the split (hi/lo bf16) residual GEMM with a TMA epilogue and <= 4 N tiles");
     return cudaErrorInvalidValue;
   }
   if (ln_cons && (!ts || kp.epi.ln_c1 == nullptr || kp.epi.ln_parts <= 0 || kp.epi.ln_dim <= 0)) {
@@ -1133,14 +1138,20 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
     else
       fn = kp.pair ? gemm_tc_kernel<OUT_F32, ACT_NONE, true, true, 4, true> : gemm_tc_kernel<OUT_F32, ACT_NONE, true, false, 4, true>;
     const long long res_rows = kp.epi.res_mod > 0 ? kp.epi.res_mod : kp.M;
-    if (!make_tmap_f32_chunk(&kp.tmR, kp.epi.residual, res_rows, kp.N, kp.epi.ldr)) return cudaErrorInvalidValue;
-    if (!make_tmap_f32_chunk(&kp.tmC, kp.epi.out, kp.M, kp.N, kp.epi.ldc)) return cudaErrorInvalidValue;
     if (ln_prod) {
-      const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kp.N), static_cast<cuuint64_t>(kp.M)};
-      const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kp.epi.ldxb) * 2};
-      const cuuint32_t box[2] = {32, 32};
-      if (!make_tmap_bf16(&kp.tmCb, kp.epi.ln_xb_out, 2, dims, strides, box, 64)) return cudaErrorInvalidValue;
+      auto split_map = [&](CUtensorMap* m, const void* base, long long rows, int ld) {
+        const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kp.N), static_cast<cuuint64_t>(rows)};
+        const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+        const cuuint32_t box[2] = {32, 128};
+        return make_tmap_bf16(m, base, 2, dims, strides, box, 64);
+      };
+      if (!split_map(&kp.tmR, kp.epi.residual, res_rows, kp.epi.ldr) || !split_map(&kp.tmR2, kp.epi.residual_lo, res_rows, kp.epi.ldr) ||
+          !split_map(&kp.tmC, kp.epi.out, kp.M, kp.epi.ldc) || !split_map(&kp.tmC2, kp.epi.out_lo, kp.M, kp.epi.ldc))
+        return cudaErrorInvalidValue;
       if (kp.epi.ln_parts_out) *kp.epi.ln_parts_out = kp.num_n_tiles;
+    } else {
+      if (!make_tmap_f32_chunk(&kp.tmR, kp.epi.residual, res_rows, kp.N, kp.epi.ldr)) return cudaErrorInvalidValue;
+      if (!make_tmap_f32_chunk(&kp.tmC, kp.epi.out, kp.M, kp.N, kp.epi.ldc)) return cudaErrorInvalidValue;
     }
   } else if (ts) {
     fn = kp.pair ? select_kernel_ts<true>(kp.epi, ew) : select_kernel_ts<false>(kp.epi, ew);
@@ -1172,7 +1183,7 @@ cudaError_t launch(KParams& kp, cudaStream_t s, double flops) {
   }
   TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), 227 * 1024));
   const int threads = 64 + 32 * ew + (te ? 64 : 0);
-  const int staging = te ? kResSlots * kResSlotBytes + (ln_prod ? kLnCopyBytes : 0)
+  const int staging = te ? kResSlots * kResSlotBytes
                          : ts ? ew * (ew == 16 ? 1 : 2) * (2048 + (kp.epi.pool_mode ? 512 : 0)) : ew * 2048;
   const int slots = kp.pair ? max_pairs(reinterpret_cast<const void*>(fn), 200 * 1024, threads) : num_sms();
   if (kp.b_resident && (num_kb * b_bytes > (kp.pair ? kResidentMaxPair : kp.halo ? kHaloResidentMax : kResidentMax) || kp.num_n_tiles > slots)) kp.b_resident = 0;
@@ -1251,6 +1262,13 @@ cudaError_t check_epilogue(const Epilogue& e, int N, int BN) {
   if (e.out_type == OUT_F32 && (e.ldc % 4 != 0 || N % 16 != 0)) {
     set_error("gemm: fp32 output needs ldc % 4 == 0 and N % 16 == 0");
     return cudaErrorInvalidValue;
+  }
+  if (e.out_type == OUT_SPLIT || e.res_type == RES_SPLIT) {
+    if (e.out_type != OUT_SPLIT || e.res_type != RES_SPLIT || e.ln_stats_out == nullptr || e.act != ACT_NONE || N % 16 != 0) {
+      set_error("gemm: the split (hi/lo bf16) residual stream is RES_SPLIT in, OUT_SPLIT out, with LayerNorm statistics");
+      return cudaErrorInvalidValue;
+    }
+    return cudaSuccess;
   }
   if (e.res_type != RES_NONE && (e.res_type != RES_F32 || e.out_type != OUT_F32 || e.ldr % 4 != 0)) {
     set_error("gemm: the residual path is fp32 in / fp32 out with a 16-byte aligned pitch");

@@ -12,8 +12,11 @@
 namespace tt {
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
-enum ResType : int { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2 };
-enum OutType : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_CLS_TAIL = 2 };
+enum ResType : int { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2, RES_SPLIT = 3 };
+enum OutType : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_CLS_TAIL = 2, OUT_SPLIT = 3 };
+// RES_SPLIT / OUT_SPLIT: an fp32 tensor stored as two bf16 tensors hi = bf16(x), lo = bf16(x - hi) (same bytes as fp32,
+// x = hi + lo to ~2^-17 relative).  The PARSeq encoder keeps its residual stream this way: `hi` IS the bf16 operand the
+// next GEMM reads, so the LayerNorm-fused path needs no separate bf16 copy of x.
 
 struct Epilogue {
   const float* bias = nullptr;      // [N] fp32 (BatchNorm already folded in)
@@ -37,9 +40,11 @@ struct Epilogue {
   // ---- LayerNorm fused away (PARSeq encoder: x -> LN -> Linear).  With W' = W * gamma (folded at export),
   //   Linear(LN(x))[n] = rstd * (x . W'[n]) - rstd * mean * c1[n] + c0[n],  c1[n] = sum_k W'[n][k], c0[n] = b[n] + beta . W[n]
   // so the GEMM reads the UN-normalised row as bf16 and its epilogue applies the row's (mean, rstd).
-  // Producer (fp32 out + residual, TMA epilogue): also emit bf16(x) and, per row and N tile, (sum x, sum x^2).
-  __nv_bfloat16* ln_xb_out = nullptr;  // [M][ldxb] bf16 copy of the output rows
-  int ldxb = 0;
+  // Producer (RES_SPLIT in, OUT_SPLIT out, TMA epilogue: `residual` / `out` are the hi tensors, `residual_lo` / `out_lo`
+  // the lo tensors, all bf16 with pitches ldr / ldc): x = hi + lo + acc + bias in fp32, written back split, and per row
+  // and N tile (sum x, sum x^2).
+  const void* residual_lo = nullptr;
+  void* out_lo = nullptr;
   float* ln_stats_out = nullptr;       // [M][ln_parts][2] fp32 partial sums; ln_parts = N / BN is written to *ln_parts_out
   int* ln_parts_out = nullptr;
   // Consumer (bf16 out): `bias` holds c0, ln_c1 holds c1, ln_stats_in the producer's partial sums over ln_dim columns.

@@ -275,14 +275,16 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
   static const int chunk_env = std::getenv("TT_ENC_CHUNK") ? std::atoi(std::getenv("TT_ENC_CHUNK")) : 0;
   const int chunk = chunk_env > 0 ? std::min(chunk_env, n) : n;
   const size_t Mc = static_cast<size_t>(chunk) * 128;
-  // LayerNorm fused away (gemm_tc.cuh, Epilogue::ln_*): the residual GEMMs (patch embedding, proj, fc2) also emit
-  // bf16(x) and the rows' (sum, sum of squares); qkv / fc1 / the memory K|V projection read bf16(x) with gamma folded
-  // into their weights and apply (mean, rstd) in the epilogue.  Needs the folded tensors of the current weights.py;
-  // TT_ENC_LNFUSE=0 keeps the standalone LayerNorm kernel (A/B runs, parity test).
+  // LayerNorm fused away (gemm_tc.cuh, Epilogue::ln_*): the residual stream x is kept as a bf16 pair (hi, lo) with
+  // x = hi + lo (same bytes as fp32, ~2^-17 relative); the residual GEMMs (patch embedding, proj, fc2) update it in
+  // fp32 and emit the rows' (sum, sum of squares); qkv / fc1 / the memory K|V projection read `hi` (= bf16(x)) with
+  // gamma folded into their weights and apply (mean, rstd) in the epilogue.  Needs the folded tensors of the current
+  // weights.py; TT_ENC_LNFUSE=0 keeps the fp32 stream and the standalone LayerNorm kernel (A/B runs, parity test).
   const char* lnf_env = std::getenv("TT_ENC_LNFUSE");
   const bool lnf = !(lnf_env && std::atoi(lnf_env) == 0) && wf.has("b0.qkv.wf") && wf.has("dec.ca.kvf.wf");
-  ARENA_GET(x, float, Mc * D);       // fp32 residual stream
-  ARENA_GET(h, bf, Mc * D);          // LayerNorm output (unfused) / bf16 copy of x (fused)
+  ARENA_GET(x, float, Mc * D);       // fp32 residual stream (unfused) / the lo half of the split stream (fused; first half of the buffer)
+  ARENA_GET(h, bf, Mc * D);          // LayerNorm output (unfused) / the hi half of the split stream = bf16(x) (fused)
+  bf* const x_lo = reinterpret_cast<bf*>(x);
   ARENA_GET(qkv, bf, Mc * 3 * D);
   ARENA_GET(att, bf, Mc * D);
   ARENA_GET(hid, bf, Mc * pd.mlp);
@@ -292,13 +294,22 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
 
   // residual GEMM x (+)= A W^T + b [+ table]; fused mode: also bf16(x) -> h and the LayerNorm partial sums
   int ln_parts = 0;
+  // res == nullptr: the stream itself (in place); else a positional table (fp32 unfused / split pair fused) of res_mod rows
   auto res_gemm = [&](const bf* A, int lda, int Mi, int K, const bf* W, const float* bias, const float* res, int res_mod) -> cudaError_t {
     LinearProblem l;
     l.A = A; l.lda = lda; l.M = Mi; l.K = K; l.W = W; l.N = D;
     Epilogue e;
-    e.bias = bias; e.residual = res; e.res_type = RES_F32; e.ldr = D; e.res_mod = res_mod;
-    e.out = x; e.out_type = OUT_F32; e.ldc = D;
-    if (lnf) { e.ln_xb_out = h; e.ldxb = D; e.ln_stats_out = lnstats; e.ln_parts_out = &ln_parts; }
+    e.bias = bias; e.ldr = D; e.res_mod = res_mod; e.ldc = D;
+    if (lnf) {
+      const bf* tab = w->pos_split;
+      e.res_type = RES_SPLIT; e.out_type = OUT_SPLIT;
+      e.residual = res ? tab : h; e.residual_lo = res ? tab + static_cast<size_t>(res_mod) * D : x_lo;
+      e.out = h; e.out_lo = x_lo;
+      e.ln_stats_out = lnstats; e.ln_parts_out = &ln_parts;
+    } else {
+      e.residual = res ? res : x; e.res_type = RES_F32;
+      e.out = x; e.out_type = OUT_F32;
+    }
     return linear_forward(l, e, s);
   };
   // y = Linear(LN(x)) [GELU]: fused mode reads h = bf16(x) with the folded weights `name`.wf / .c0 / .c1
@@ -324,10 +335,10 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
       if (!lnf) RUN(layernorm(x, Mi, D, wf.f32(p + "ln1.g"), wf.f32(p + "ln1.b"), 1e-6f, h, nullptr, 0, s));
       RUN(ln_gemm(p + "qkv", Mi, 3 * D, ACT_NONE, qkv));
       RUN(attention_enc(qkv, att, nc, D, pd.enc_heads, s));
-      RUN(res_gemm(att, D, Mi, D, wf.bf(p + "proj.w"), wf.f32(p + "proj.b"), x, 0));
+      RUN(res_gemm(att, D, Mi, D, wf.bf(p + "proj.w"), wf.f32(p + "proj.b"), nullptr, 0));
       if (!lnf) RUN(layernorm(x, Mi, D, wf.f32(p + "ln2.g"), wf.f32(p + "ln2.b"), 1e-6f, h, nullptr, 0, s));
       RUN(ln_gemm(p + "fc1", Mi, pd.mlp, ACT_GELU, hid));
-      RUN(res_gemm(hid, pd.mlp, Mi, pd.mlp, wf.bf(p + "fc2.w"), wf.f32(p + "fc2.b"), x, 0));
+      RUN(res_gemm(hid, pd.mlp, Mi, pd.mlp, wf.bf(p + "fc2.w"), wf.f32(p + "fc2.b"), nullptr, 0));
     }
     // cross-attention K/V of the memory = rows D.. of cross_attn.in_proj applied to the encoder's final LayerNorm, once per crop
     bf* mkv = mem_kv + static_cast<size_t>(c0) * 128 * 2 * D;
@@ -437,6 +448,7 @@ DeviceWeights::~DeviceWeights() {
   if (q_sa_table) cudaFree(q_sa_table);
   if (kv_table) cudaFree(kv_table);
   if (sc_table) cudaFree(sc_table);
+  if (pos_split) cudaFree(pos_split);
   dec_dense_free(&dd);
 }
 
@@ -517,6 +529,8 @@ cudaError_t DeviceCtx::init(const std::string& dir, std::shared_ptr<DeviceWeight
     }
     TT_CUDA_TRY(stream_sync(stream));   // `tok` must outlive the copy
   }
+  TT_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w->pos_split), sizeof(__nv_bfloat16) * 2 * 128 * D));
+  RUN(split_f32(wf.f32("pos"), 128LL * D, w->pos_split, w->pos_split + 128 * D, stream));
   TT_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&w->sc_table), sizeof(float) * L * L * NT * pd.dec_heads));
   RUN(dec_score_table(w->q_sa_table, w->kv_table, L, NT, D, pd.dec_heads, w->sc_table, stream));
   // fused decoder kernels: weight tensor maps + per-column vectors

@@ -792,6 +792,16 @@ __global__ void k_argmax(const float* __restrict__ logits, int rows, int n_cls, 
   }
 }
 
+// fp32 -> (hi, lo) bf16 pair with x ~= hi + lo (the split residual stream of gemm_tc.cuh, RES_SPLIT)
+__global__ void k_split_f32(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  const __nv_bfloat16 h = __float2bfloat16(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16(v - __bfloat162float(h));
+}
+
 __global__ void k_patchify(const uint8_t* __restrict__ crops, int n, __nv_bfloat16* __restrict__ out) {
   const int dy = blockIdx.x, b = blockIdx.y, dx = threadIdx.x;
   const uint8_t* p = crops + ((static_cast<size_t>(b) * 32 + dy) * 128 + dx) * 3;
@@ -930,6 +940,13 @@ cudaError_t argmax_rows(const float* logits, int rows, int n_cls, int ld, int* i
   if (rows <= 0) return cudaSuccess;
   k_argmax<<<(rows + 7) / 8, 256, 0, s>>>(logits, rows, n_cls, ld, ids, ids_stride, next, next_stride, forced,
                                           forced_stride);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t split_f32(const float* x, long long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_split_f32<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(x, n, hi, lo);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -55,6 +55,8 @@ cudaError_t argmax_rows(const float* logits, int rows, int n_cls, int ld, int* i
                         int* next_tokens, int next_stride, const int* forced, int forced_stride, cudaStream_t s);
 // u8 crops [n][32][128][3] -> bf16 patch rows [n*128][96] (raw 0..255), k = c*32 + (y%4)*8 + x%8
 cudaError_t tokens_init(int* tokens, int n, int L, int bos, int pad, cudaStream_t s);
+// x fp32 [n] -> hi = bf16(x), lo = bf16(x - hi)  (split residual stream, gemm_tc.cuh RES_SPLIT)
+cudaError_t split_f32(const float* x, long long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t s);
 cudaError_t patchify_u8(const uint8_t* crops, int n, __nv_bfloat16* out, cudaStream_t s);
 
 }  // namespace tt
