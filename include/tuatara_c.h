@@ -47,8 +47,9 @@ typedef struct tt_config {
   int min_area;         /* 10    tuatara.cpp:148 */
   int max_batch_pages;  /* pages whose crops form one PARSeq batch in a slot (0 = default 32); detection runs in units of <= 8
                            equally sized pages, crops of pages of any size share the recognition batch */
-  int slots_per_gpu;    /* concurrent execution slots (streams + host threads) per GPU: 0 = default 2, max 4.  Two slots
-                           overlap one batch's host phases with another batch's kernels (+5 %); 1 = strictly serial kernels */
+  int slots_per_gpu;    /* concurrent execution slots (streams + host threads) per GPU: 0 = default 3, max 4.  More slots
+                           overlap one batch's host phases and latency-bound kernels with another batch's kernels
+                           (2 slots +16 %, 3 slots +19 % over 1 on the 512-page bench); 1 = strictly serial kernels */
   int rectify;          /* 0 (default) = the reference's axis-aligned boundingRect crop (tuatara.cpp:416).  1 = opt-in for the
                            TODO at tuatara.cpp:411-415: each crop is the perspective warp of its rotated box to 128 x 32
                            (cv::getPerspectiveTransform + cv::warpPerspective semantics); boxes / bboxes are unchanged */

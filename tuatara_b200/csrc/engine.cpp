@@ -436,7 +436,7 @@ int tt_ocr_pages_ex(tt_engine* e, const tt_image* pages, int n_pages, const tt_o
     }
     static const int env_slots = std::getenv("TT_SLOTS") ? std::atoi(std::getenv("TT_SLOTS")) : 0;  // development override
     const int cfg_slots = e->slots.load();
-    const int want = std::max(1, std::min(cfg_slots > 0 ? cfg_slots : env_slots > 0 ? env_slots : 2, kSlotsPerDevice));
+    const int want = std::max(1, std::min(cfg_slots > 0 ? cfg_slots : env_slots > 0 ? env_slots : 3, kSlotsPerDevice));
     // workers: device-major round robin, so that a short request touches every GPU before any second slot
     struct W { int g, sidx; };
     std::vector<W> ws;
