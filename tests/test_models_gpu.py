@@ -82,6 +82,23 @@ def test_craft_fused_maxpool_is_bit_identical(engine, monkeypatch):
         assert np.array_equal(fused, plain), (h, w)
 
 
+def test_craft_conv1_1_from_u8_matches_the_gemm_path(engine, monkeypatch):
+    """conv1_1 straight from the u8 page (mma.sync, A fragments built from a smem halo) against the round-1 path (im2col
+    tensor + K = 32 tcgen05 GEMM): the same bf16 products accumulated in fp32 in another order, so relu2_2 -- two
+    convolutions downstream -- agrees to rounding noise, and the maps stay inside their oracle tolerance either way."""
+    for h, w in ((640, 768), (608, 352)):
+        craft_in, _ = tb.preprocess(synth.synth_page(8)[:h, :w])
+        new = engine.craft_forward(craft_in)
+        t_new = engine.craft_tap("relu2_2")
+        monkeypatch.setenv("TT_CRAFT_C11", "0")
+        old = engine.craft_forward(craft_in)
+        t_old = engine.craft_tap("relu2_2")
+        monkeypatch.delenv("TT_CRAFT_C11")
+        e_tap, e_map = _rel_l2(t_new, t_old), _rel_l2(new, old)
+        print("conv1_1 u8 vs gemm path: relu2_2 rel-L2", e_tap, "maps rel-L2", e_map)
+        assert e_tap <= 2e-3 and e_map <= 1e-2
+
+
 def _crops(n, seed=0):
     img = synth.synth_page(seed)
     rng = np.random.default_rng(seed)

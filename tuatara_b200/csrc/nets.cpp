@@ -152,10 +152,15 @@ cudaError_t DeviceCtx::craft_forward(const uint8_t* in, int B, int H, int W, flo
 #define CV(...) do { cudaError_t _e = conv(__VA_ARGS__); if (_e != cudaSuccess) return _e; } while (0)
 #define RUN(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return _e; } while (0)
 
-  ARENA_GET(x0, bf, px * 32);
-  RUN(page_im2col(in, B, H, W, x0, s));
   ARENA_GET(a1, bf, px * 64);
-  CV("c1_1", x0, 32, nullptr, 0, H, W, 1, 1, 64, true, a1);  // 3x3 conv as a K=32 GEMM over the im2col'd pixels
+  const char* c11_env = std::getenv("TT_CRAFT_C11");   // 0: the round-1 path (im2col tensor + K=32 tcgen05 GEMM), A/B runs
+  if (c11_env && std::atoi(c11_env) == 0) {
+    ARENA_GET(x0, bf, px * 32);
+    RUN(page_im2col(in, B, H, W, x0, s));
+    CV("c1_1", x0, 32, nullptr, 0, H, W, 1, 1, 64, true, a1);  // 3x3 conv as a K=32 GEMM over the im2col'd pixels
+  } else {
+    RUN(conv1_1_u8(in, B, H, W, w->craft.bf("c1_1.w"), w->craft.f32("c1_1.b"), a1, s));   // straight from the u8 page
+  }
   ARENA_GET(p1, bf, px / 4 * 64);
   RUN(conv_pool("c1_2", a1, 64, H, W, 64, nullptr, p1));
   ARENA_GET(b1, bf, px / 4 * 128);

@@ -6,6 +6,8 @@
 #include <cuda.h>
 #include <math.h>
 
+#include <algorithm>
+
 #include <cstdlib>
 
 #include "common.h"
@@ -108,6 +110,159 @@ __global__ void k_upsample2(const __nv_bfloat16* __restrict__ in, __nv_bfloat16*
     for (int k = 0; k < 8; ++k)
       o[k] = (1.f - ly) * ((1.f - lx) * a[k] + lx * bb[k]) + ly * ((1.f - lx) * cc[k] + lx * d[k]);
     st8(out + i * 8, pack8(o));
+  }
+}
+
+// conv1_1 (3 -> 64, 3x3, + folded BN + ReLU) straight from the u8 page.  Round 1 ran it as a K = 32 tcgen05 GEMM over a
+// 64 B/pixel im2col tensor that a separate kernel wrote (70 TFLOP/s; 0.51 ms per 8 pages for a layer whose floor is
+// its 128 B/pixel output write, 0.17 ms).  Here a CTA builds the im2col rows of its 16 x 32-pixel tile in smem from a
+// u8 halo (each thread one pixel: 27 bytes -> one 64-byte K-major SWIZZLE_64B operand row), one warp issues
+// 4 x 2 tcgen05.mma (M = 128 pixels, N = 64, K = 16) into TMEM, and the epilogue (bias, ReLU, bf16) leaves through
+// SWIZZLE_128B tiles and TMA stores (image edges clipped by the TMA unit).
+//   wt: bf16 [64][32], k = (dy * 3 + dx) * 3 + c (k 27..31 zero), already scaled by 1/255.
+constexpr int kC11TileH = 16, kC11TileW = 32, kC11HaloW = kC11TileW + 2;
+constexpr int kC11Halo = (kC11TileH + 2) * kC11HaloW * 3;                 // 1836 bytes
+constexpr int kC11Smem = 4 * 16384 /* out */ + 4 * 8192 /* A */ + 4096 /* W */ + 2048 /* halo */ + 256 /* bias */ + 64 + 1024;
+__global__ void __launch_bounds__(256) k_conv1_1(const uint8_t* __restrict__ img, int H, int W, int n_tiles,
+                                                 const __nv_bfloat16* __restrict__ wt, const float* __restrict__ bias,
+                                                 const __grid_constant__ CUtensorMap tm_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sO = smem;                       // 4 m-tiles x [128 pixels][128 B], SWIZZLE_128B (TMA store source)
+  uint8_t* sA = sO + 4 * 16384;             // 4 m-tiles x [128 pixels][32 k] bf16, K-major SWIZZLE_64B
+  uint8_t* sW = sA + 4 * 8192;              // [64 couts][32 k] bf16, K-major SWIZZLE_64B
+  uint8_t* sHalo = sW + 4096;
+  float* sBias = reinterpret_cast<float*>(sHalo + 2048);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sBias + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int tiles_x = (W + kC11TileW - 1) / kC11TileW, tiles_y = (H + kC11TileH - 1) / kC11TileH;
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tm_out);
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 256);
+  {  // weights (swizzled as the MMA reads them): 64 rows x 4 chunks of 16 B; bias
+    const int row = tid >> 2, ch = tid & 3;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(wt + row * 32) + ch);
+    *reinterpret_cast<uint4*>(sW + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4)) = v;
+  }
+  if (tid < 64) sBias[tid] = __ldg(bias + tid);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  // A thread's bytes of a tile's (16 + 2) x (32 + 2) x 3 halo, all requested before any is used.  Persistent CTAs: the
+  // NEXT tile's halo is in flight while this one is computed (rolled into a per-CTA loop of dependent loads the kernel
+  // was latency bound: 490 us per 8 pages; one tile per CTA with the loads unrolled: 365 us).
+  constexpr int kIters = (kC11Halo + 255) / 256;
+  auto load_halo = [&](int tile, uint8_t (&hv)[kIters]) {
+    const int b = tile / (tiles_x * tiles_y), t = tile - b * tiles_x * tiles_y;
+    const int y0 = (t / tiles_x) * kC11TileH, x0 = (t % tiles_x) * kC11TileW;
+    const uint8_t* base = img + static_cast<size_t>(b) * H * W * 3;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int i = it * 256 + tid;
+      const int c = i % 3, px = i / 3;
+      const int hx = px % kC11HaloW, hy = px / kC11HaloW;
+      const int y = y0 + hy - 1, x = x0 + hx - 1;
+      hv[it] = (i < kC11Halo && y >= 0 && y < H && x >= 0 && x < W) ? __ldg(base + (static_cast<size_t>(y) * W + x) * 3 + c) : 0;   // zero padding
+    }
+  };
+  uint8_t hv[kIters];
+  if (static_cast<int>(blockIdx.x) < n_tiles) load_halo(blockIdx.x, hv);
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / (tiles_x * tiles_y), t = tile - b * tiles_x * tiles_y;
+    const int y0 = (t / tiles_x) * kC11TileH, x0 = (t % tiles_x) * kC11TileW;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int i = it * 256 + tid;
+      if (i < kC11Halo) sHalo[i] = hv[it];
+    }
+    __syncthreads();
+    if (tile + static_cast<int>(gridDim.x) < n_tiles) load_halo(tile + gridDim.x, hv);
+    // im2col rows: pixel p of the tile (2 per thread) -> row (p % 128) of m-tile p / 128; m-tile = 4 image rows x 32 columns
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int p = pass * 256 + tid;
+      const int ty = p >> 5, tx = p & 31, mt = p >> 7, r = p & 127;
+      const uint8_t* h0 = sHalo + (ty * kC11HaloW + tx) * 3;     // tap (0, 0) of this pixel; a tap row is 9 consecutive bytes
+      float v[32];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) v[dy * 9 + j] = static_cast<float>(h0[dy * kC11HaloW * 3 + j]);
+#pragma unroll
+      for (int k = 27; k < 32; ++k) v[k] = 0.f;
+      uint8_t* arow = sA + mt * 8192 + r * 64;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint4 o;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * ch + 0], v[8 * ch + 1]), t1 = __floats2bfloat162_rn(v[8 * ch + 2], v[8 * ch + 3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * ch + 4], v[8 * ch + 5]), t3 = __floats2bfloat162_rn(v[8 * ch + 6], v[8 * ch + 7]);
+        o.x = *reinterpret_cast<uint32_t*>(&t0); o.y = *reinterpret_cast<uint32_t*>(&t1);
+        o.z = *reinterpret_cast<uint32_t*>(&t2); o.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(arow + ((ch ^ ((r >> 1) & 3)) << 4)) = o;
+      }
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();   // also: every warp finished reading the previous tile's accumulators
+    if (warp == 0) {   // all lanes converged, one elected lane issues
+      ptx::tc_fence_after();
+      const uint32_t idesc = ptx::make_idesc_bf16(128, 64);
+      const uint32_t wa = ptx::smem_u32(sW);
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const uint32_t aa = ptx::smem_u32(sA + mt * 8192);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          ptx::mma_bf16_e(tmem + mt * 64, ptx::make_smem_desc(aa + k * 32, 64), ptx::make_smem_desc(wa + k * 32, 64), idesc, k != 0);
+      }
+      ptx::mma_commit_e(bar);
+    }
+    if (tid == 0) ptx::bulk_wait_read<0>();   // the previous tile's TMA stores have read sO
+    ptx::mbar_wait(bar, phase);
+    phase ^= 1;
+    ptx::tc_fence_after();
+    __syncthreads();
+    // epilogue: warp w reads TMEM lanes (w & 3) * 32 .. of m-tiles (w >> 2) * 2 and + 1
+    const int q = warp & 3, r = q * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int mt = (warp >> 2) * 2 + i;
+      uint8_t* orow = sO + mt * 16384 + r * 128;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t raw[32];
+        ptx::tmem_ld<32>(tmem + (static_cast<uint32_t>(q * 32) << 16) + mt * 64 + half * 32, raw);
+        ptx::tmem_ld_wait(raw);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = fmaxf(__uint_as_float(raw[8 * ch + e]) + sBias[half * 32 + 8 * ch + e], 0.f);
+          *reinterpret_cast<uint4*>(orow + (((half * 4 + ch) ^ (r & 7)) << 4)) = pack8(o);
+        }
+      }
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) ptx::tma_store_4d(&tm_out, sO + mt * 16384, 0, x0, y0 + mt * 4, b);   // rows / columns past the image are clipped
+      ptx::bulk_commit();
+    }
+  }
+  if (tid == 0) ptx::bulk_wait_read<0>();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, 256);
   }
 }
 
@@ -812,6 +967,26 @@ __global__ void k_patchify(const uint8_t* __restrict__ crops, int n, __nv_bfloat
 }
 
 }  // namespace
+
+cudaError_t conv1_1_u8(const uint8_t* img, int B, int H, int W, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* out,
+                       cudaStream_t s) {
+  CUtensorMap tm;
+  const cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
+  const cuuint64_t strides[3] = {128, 128ull * W, 128ull * W * H};
+  const cuuint32_t box[4] = {64, kC11TileW, 4, 1};
+  if (!make_tmap_bf16(&tm, out, 4, dims, strides, box, 128)) return cudaErrorInvalidValue;
+  TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(k_conv1_1), kC11Smem));
+  const int n_tiles = B * ((W + kC11TileW - 1) / kC11TileW) * ((H + kC11TileH - 1) / kC11TileH);
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  k_conv1_1<<<std::min(n_tiles, 2 * sms), 256, kC11Smem, s>>>(img, H, W, n_tiles, wt, bias, tm);   // 2 persistent CTAs per SM (105 KB smem, 256 TMEM columns each)
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
 
 cudaError_t maxpool2x2(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s) {
   const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 8);

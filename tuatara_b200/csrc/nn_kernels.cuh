@@ -8,6 +8,10 @@
 namespace tt {
 
 // ---- CRAFT (NHWC bf16) -------------------------------------------------------------------
+// conv1_1 + BN + ReLU from the u8 page [B][H][W][3] (already channel-swapped, raw 0..255): wt bf16 [64][32] with
+// k = tap * 3 + c and the 1/255 folded in (weights.py "c1_1.w"), out bf16 NHWC [B][H][W][64]
+cudaError_t conv1_1_u8(const uint8_t* img, int B, int H, int W, const __nv_bfloat16* wt, const float* bias, __nv_bfloat16* out,
+                       cudaStream_t s);
 // MaxPool2d(2, 2): [B][H][W][C] -> [B][H/2][W/2][C]           (vgg16_bn features 6/13/23/33)
 cudaError_t maxpool2x2(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t s);
 // MaxPool2d(3, stride 1, pad 1)                                 (slice5[0])
