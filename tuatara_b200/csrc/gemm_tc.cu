@@ -74,7 +74,7 @@ struct KParams {
                    // feeds all 9 taps (A operand = the staged tile read at a pixel offset); 0 = one TMA box per tap
   int stages;
   int b_resident;  // 1: the CTA's [BN x K] weight slice is loaded once and stays in smem; only A streams
-  int debug;       // TT_GEMM_DEBUG (development only): 1 = skip epilogue stores, 2 = skip TMEM loads + math + stores
+  int debug;       // TT_GEMM_DEBUG (development only): 1 = skip epilogue stores, 2 = skip TMEM loads + math + stores, 8 = legacy epilogue preamble (A/B)
   unsigned long long* dbg_out;  // TT_GEMM_DEBUG & 4: per-role wait/busy cycle counters of CTA 0
   uint32_t* trace;              // TT_TRACE=1 (trace.h): host-mapped progress buffer, nullptr otherwise
   uint32_t serial;              //   launch serial inside it
@@ -503,55 +503,73 @@ __global__ void __launch_bounds__(64 + 32 * EW + (TE ? 64 : 0), 1) gemm_tc_kerne
     TileIter it(p);
     float bias_cur[kBiasPer], c1_cur[kBiasPer];
     bias_fetch(it, bias_cur, c1_cur);
-    // LayerNorm consumer: (sum, sum of squares) of this thread's row in tile t, summed over the producer's partials
-    float ln_s1n = 0.f, ln_s2n = 0.f;
-    auto ln_fetch = [&](const TileIter& t, float& s1, float& s2) {
-      s1 = 0.f; s2 = 0.f;
+    // LayerNorm consumer: the producer's (sum, sum of squares) partials of this thread's row in tile t.  They are requested
+    // one tile ahead and only LOADED here -- the sums are formed where they are used, one tile later: an add right behind
+    // the load parks the (in-order) warp on the L2 round trip before it reaches the accumulator wait, every tile.
+    constexpr int kLnMaxParts = 4;   // the producer has <= 4 N tiles (launch())
+    float2 ln_raw[kLnMaxParts];
+#pragma unroll
+    for (int pp = 0; pp < kLnMaxParts; ++pp) ln_raw[pp] = make_float2(0.f, 0.f);
+    auto ln_fetch = [&](const TileIter& t) {
       if constexpr (kLNA) {
+        bool ok = false;
+        const float2* st = nullptr;
         if (t.valid()) {
           const int mt = PAIR ? t.m_tile(p) * 2 + static_cast<int>(rank) : t.m_tile(p);
           const long long mrow = static_cast<long long>(mt) * kBlockM + r;
-          if (mrow < M && (!PAIR || mt < p.m_tiles_total)) {
-            const float2* st = reinterpret_cast<const float2*>(p.epi.ln_stats_in) + mrow * p.epi.ln_parts;
-            for (int pp = 0; pp < p.epi.ln_parts; ++pp) { const float2 v = __ldg(st + pp); s1 += v.x; s2 += v.y; }
-          }
+          ok = mrow < M && (!PAIR || mt < p.m_tiles_total);
+          st = reinterpret_cast<const float2*>(p.epi.ln_stats_in) + mrow * p.epi.ln_parts;
         }
+#pragma unroll
+        for (int pp = 0; pp < kLnMaxParts; ++pp)
+          ln_raw[pp] = (ok && pp < p.epi.ln_parts) ? __ldg(st + pp) : make_float2(0.f, 0.f);
+        if (p.debug & 8) asm volatile("" ::"f"(ln_raw[0].x), "f"(ln_raw[1].x));   // A/B: wait for the loads here, as the eager sums did
       }
     };
-    ln_fetch(it, ln_s1n, ln_s2n);
-    (void)ln_s1n; (void)ln_s2n;
+    ln_fetch(it);
+    (void)ln_raw;
     const uint32_t c1_s = ptx::smem_u32(&ctl->c1[0][0]);
     (void)c1_s;
     int te_slot = 0;
     uint32_t te_ph = 0;
     (void)te_slot; (void)te_ph;
+    int staged_n0 = -1, staged_n1 = -1;   // N tile whose bias / c1 vectors sit in smem slot 0 / 1
     for (; it.valid(); it.next()) {
       const int n_tile = it.n_tile(p), m_tile = PAIR ? it.m_tile(p) * 2 + static_cast<int>(rank) : it.m_tile(p);
       const int n0 = n_tile * BN;
       {
+        // A weight-resident CTA keeps one N slice for its whole life: after the first two tiles both slots already hold
+        // this slice's vectors, and the staging + the barrier over all epilogue warps (a rendezvous per tile) are skipped.
+        // The branch is uniform over the CTA: every warp walks the same tile sequence.
+        if ((as ? staged_n1 : staged_n0) != n_tile || (p.debug & 8)) {
 #pragma unroll
-        for (int i = 0; i < kBiasPer; ++i)
-          if (bias_t + i * 32 * EW < BN) {
-            ptx::sts32(bias_s + (as * 256 + bias_t + i * 32 * EW) * 4, __float_as_uint(bias_cur[i]));
-            if constexpr (kLNA) ptx::sts32(c1_s + (as * 256 + bias_t + i * 32 * EW) * 4, __float_as_uint(c1_cur[i]));
-          }
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");  // epilogue warps only
+          for (int i = 0; i < kBiasPer; ++i)
+            if (bias_t + i * 32 * EW < BN) {
+              ptx::sts32(bias_s + (as * 256 + bias_t + i * 32 * EW) * 4, __float_as_uint(bias_cur[i]));
+              if constexpr (kLNA) ptx::sts32(c1_s + (as * 256 + bias_t + i * 32 * EW) * 4, __float_as_uint(c1_cur[i]));
+            }
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");  // epilogue warps only
+          if (as) staged_n1 = n_tile; else staged_n0 = n_tile;
+        }
         TileIter nx = it;
         nx.next();
-        bias_fetch(nx, bias_cur, c1_cur);
+        if (nx.valid() && nx.n_tile(p) != (as ? staged_n0 : staged_n1)) bias_fetch(nx, bias_cur, c1_cur);
       }
       uint64_t ln_a = 0ull, ln_b = 0ull;   // LayerNorm consumer: (rstd, rstd) and (-rstd * mean, -rstd * mean) of this thread's row
       (void)ln_a; (void)ln_b;
       if constexpr (kLNA) {
         // this tile's sums were requested one tile ago (ln_s1n / ln_s2n): their latency hides behind the previous tile
         const float inv_d = 1.f / static_cast<float>(p.epi.ln_dim);
+        float ln_s1n = 0.f, ln_s2n = 0.f;   // same summation order as before: partial 0, 1, ...
+#pragma unroll
+        for (int pp = 0; pp < kLnMaxParts; ++pp) { ln_s1n += ln_raw[pp].x; ln_s2n += ln_raw[pp].y; }
         const float mu = ln_s1n * inv_d;
         const float rstd = rsqrtf(fmaxf(ln_s2n * inv_d - mu * mu, 0.f) + p.epi.ln_eps);
         ln_a = pk2(rstd, rstd);
         ln_b = pk2(-rstd * mu, -rstd * mu);
         TileIter nx2 = it;
         nx2.next();
-        ln_fetch(nx2, ln_s1n, ln_s2n);
+        ln_fetch(nx2);
       }
       if constexpr (TE) {
         // out = residual + (acc + bias), chunk by chunk: this thread's row of the chunk sits at r*128 in the slot,

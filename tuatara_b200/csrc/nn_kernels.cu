@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 #include "common.h"
+#include "epi_math.cuh"
 #include "gemm_tc.cuh"
 #include "ptx.cuh"
 #include "trace.h"
@@ -337,9 +338,14 @@ struct AttnCtl {
 };
 constexpr int kAttnSmem = 3 * 16384 + 1024 + 64;
 
-__global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtensorMap tm_qkv,
-                                                  __nv_bfloat16* __restrict__ out, int D, float scale_log2e,
-                                                  uint32_t* trace, uint32_t serial) {
+// ONEPASS: the thread's whole S row (128 fp32) is pulled out of TMEM once and kept in registers for the maximum
+// and the exponentials (3 CTAs per SM at <= 168 registers); the two-pass form (4 CTAs per SM) reads S twice and was
+// paced by the TMEM read port: 160 KB per CTA at ~64 B/cycle/SM is 2500 of the 3550 cycles an SM spent per CTA
+// (profiles/r2_attn_enc.md), ahead of HBM (64 KB per CTA).
+template <bool ONEPASS>
+__global__ void __launch_bounds__(128, ONEPASS ? 3 : 4) k_attn_enc(const __grid_constant__ CUtensorMap tm_qkv,
+                                                                   __nv_bfloat16* __restrict__ out, int D, float scale_log2e,
+                                                                   uint32_t* trace, uint32_t serial) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -386,41 +392,69 @@ __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtens
 
   // softmax over this thread's row (row == TMEM lane == tid)
   const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  float mx = -INFINITY;
-#pragma unroll
-  for (int ch = 0; ch < 8; ++ch) {
-    uint32_t raw[16];
-    ptx::tmem_ld16(t_row + ch * 16, raw);
-    ptx::tmem_ld_wait(raw);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
-  }
   float sum = 0.f;
   const int r = tid;
-#pragma unroll
-  for (int ch = 0; ch < 8; ++ch) {
-    uint32_t raw[16];
-    ptx::tmem_ld16(t_row + ch * 16, raw);
-    ptx::tmem_ld_wait(raw);
-    float p[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      p[i] = exp2f((__uint_as_float(raw[i]) - mx) * scale_log2e);
-      sum += p[i];
-    }
-    // P as the A operand of the second MMA: K-major SWIZZLE_128B, keys [64b, 64b+64) in atom block b
+  // P as the A operand of the second MMA: K-major SWIZZLE_128B, keys [64b, 64b+64) in atom block b
+  auto store_p16 = [&](int ch, const float (&p)[16]) {
     uint8_t* blk = sP + (ch >> 2) * 16384 + r * 128;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int chunk = ((ch & 3) * 2 + h) ^ (r & 7);
       uint4 u;
-      __nv_bfloat162 t0 = __floats2bfloat162_rn(p[8 * h + 0], p[8 * h + 1]);
-      __nv_bfloat162 t1 = __floats2bfloat162_rn(p[8 * h + 2], p[8 * h + 3]);
-      __nv_bfloat162 t2 = __floats2bfloat162_rn(p[8 * h + 4], p[8 * h + 5]);
-      __nv_bfloat162 t3 = __floats2bfloat162_rn(p[8 * h + 6], p[8 * h + 7]);
-      u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
-      u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
+      u.x = pack_bf16(p[8 * h + 0], p[8 * h + 1]); u.y = pack_bf16(p[8 * h + 2], p[8 * h + 3]);
+      u.z = pack_bf16(p[8 * h + 4], p[8 * h + 5]); u.w = pack_bf16(p[8 * h + 6], p[8 * h + 7]);
       *reinterpret_cast<uint4*>(blk + chunk * 16) = u;
+    }
+  };
+  if constexpr (ONEPASS) {
+    uint32_t raw[4][32];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) ptx::tmem_ld<32>(t_row + b * 32, raw[b]);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) ptx::tmem_ld_wait(raw[b]);
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[b][i]));
+    const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    const float nms = -mx * scale_log2e;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      float p[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        // exp2((s - mx) * scale) as one FFMA + one MUFU (arguments <= 0: no range fix-up needed)
+        const float a = fmaf(__uint_as_float(raw[ch >> 1][(ch & 1) * 16 + i]), scale_log2e, nms);
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p[i]) : "f"(a));
+        s4[i & 3] += p[i];
+      }
+      store_p16(ch, p);
+    }
+    sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  } else {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      uint32_t raw[16];
+      ptx::tmem_ld16(t_row + ch * 16, raw);
+      ptx::tmem_ld_wait(raw);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+    }
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      uint32_t raw[16];
+      ptx::tmem_ld16(t_row + ch * 16, raw);
+      ptx::tmem_ld_wait(raw);
+      float p[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        p[i] = exp2f((__uint_as_float(raw[i]) - mx) * scale_log2e);
+        sum += p[i];
+      }
+      store_p16(ch, p);
     }
   }
   // generic-proxy smem writes -> visible to the tensor core (async proxy); all S reads retired
@@ -445,16 +479,20 @@ __global__ void __launch_bounds__(128) k_attn_enc(const __grid_constant__ CUtens
   ptx::tc_fence_after();
   const float inv = 1.f / sum;
   __nv_bfloat16* orow = out + (static_cast<long long>(crop) * 128 + r) * D + head * 64;
+  {
+    uint32_t raw[2][32];
+    ptx::tmem_ld<32>(t_row, raw[0]);
+    ptx::tmem_ld<32>(t_row + 32, raw[1]);
+    ptx::tmem_ld_wait(raw[0]);
+    ptx::tmem_ld_wait(raw[1]);
 #pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    uint32_t raw[16];
-    ptx::tmem_ld16(t_row + ch * 16, raw);
-    ptx::tmem_ld_wait(raw);
-    float o[16];
+    for (int ch = 0; ch < 4; ++ch) {
+      float o[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(raw[i]) * inv;
-    st8(orow + ch * 16, pack8(o));
-    st8(orow + ch * 16 + 8, pack8(o + 8));
+      for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(raw[ch >> 1][(ch & 1) * 16 + i]) * inv;
+      st8(orow + ch * 16, pack8(o));
+      st8(orow + ch * 16 + 8, pack8(o + 8));
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -1028,11 +1066,14 @@ cudaError_t attention_enc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int crop
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(3 * D) * 2};
   const cuuint32_t box[2] = {64, 128};
   if (!make_tmap_bf16(&tm, qkv, 2, dims, strides, box, 128)) return cudaErrorInvalidValue;
-  TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(k_attn_enc), kAttnSmem));
+  static const bool onepass = !(std::getenv("TT_ATTN_ONEPASS") && std::atoi(std::getenv("TT_ATTN_ONEPASS")) == 0);  // 0: A/B runs
+  const void* fn = onepass ? reinterpret_cast<const void*>(k_attn_enc<true>) : reinterpret_cast<const void*>(k_attn_enc<false>);
+  TT_CUDA_TRY(ensure_dynamic_smem(fn, kAttnSmem));
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // head_dim^-0.5 * log2(e)
   uint32_t* const trace = trace_dev();
   const uint32_t serial = trace ? trace_launch("k_attn_enc", 0 /* tracked per SM slot, not per CTA */, 128, kAttnSmem, s) : 0;
-  k_attn_enc<<<dim3(heads, crops), 128, kAttnSmem, s>>>(tm, out, D, scale_log2e, trace, serial);
+  if (onepass) k_attn_enc<true><<<dim3(heads, crops), 128, kAttnSmem, s>>>(tm, out, D, scale_log2e, trace, serial);
+  else k_attn_enc<false><<<dim3(heads, crops), 128, kAttnSmem, s>>>(tm, out, D, scale_log2e, trace, serial);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }
