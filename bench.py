@@ -46,7 +46,8 @@ WORDS = 300
 PAGE = 1280
 # SURVEY.md 8d / BASELINE.md section 3: algorithmic work per unit
 CRAFT_GFLOP_PER_PAGE = 746.0
-PARSEQ_GFLOP_PER_CROP = 6.05
+PARSEQ_GFLOP_PER_CROP = 6.05       # encoder 5.75 + decoder 0.306 (26 AR steps + refinement)
+PARSEQ_ENC_GFLOP_PER_CROP = 5.75
 
 
 def env_int(name, default):
@@ -183,6 +184,7 @@ def cpu_pipeline_sample(n_pages: int, faithful: bool = True):
     from tuatara_b200 import synth
 
     craft, parseq = make_craft(0), make_parseq("base", 0)
+    parseq.early_exit = True   # upstream PARSeq's break once every sequence of a forward() batch has an EOS (oracle/models.py)
     pages = [synth.synth_page(i) for i in range(n_pages)]
     maps = [synth.synth_score_maps(i) for i in range(n_pages)]
 
@@ -227,7 +229,7 @@ def run_reference(args, rank, world):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "synthetic 1280x1280 pages, 300 words/page, canvas 1024, score-map override",
                    "pages_per_step": 1, "note": "reference algorithm via torch CPU + cv2 (oracle/), models pre-loaded, "
-                   "PARSeq in chunks of 4 on 6 threads like tuatara.cpp:452-475"},
+                   "PARSeq in chunks of 4 on 6 threads like tuatara.cpp:452-475, upstream's AR early exit per chunk"},
         "cpu_baseline": {"value": val, "unit": "pages/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": f"1 page (300 crops) per step, {done} steps, torch threads {torch.get_num_threads()}"},
         "e2e": {"value": val, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -405,6 +407,11 @@ def run_native(args, rank, local_rank, world):
             ent.update(tflops=tf, frac_tensor=tf / peaks["tf_sustained"])
         if st["bytes"] > 0:
             ent.update(gbs=gbs, frac_hbm=gbs / peaks["hbm"])
+        if name == "parseq_decoder" and st["bytes"] > 0:
+            # the stage's bytes are one memory-K|V read (128 x 768 bf16) per pass a crop takes part in: its AR steps
+            # (per-crop early exit at EOS, as upstream PARSeq does per forward() batch) + the refinement
+            passes = st["bytes"] / (128 * 768 * 2) / (n * WORDS)
+            ent.update(early_exit=os.environ.get("TT_DEC_EARLY_EXIT", "1") != "0", ar_steps_mean=passes - 1.0, ar_steps_max=26)
         stage_lines[name] = ent
     achieved = pf / (pm / 1e3) / 1e12 if pm > 0 else 0.0
     line = {
@@ -418,6 +425,9 @@ def run_native(args, rank, local_rank, world):
                    "weights": "seeded random init (CRAFT VGG16-BN, PARSeq-base)", "parallelism": f"dp{world} (pages)",
                    "slots_per_gpu": env_int("TT_SLOTS", 3), "work_queue": "detection units of <= 8 pages pulled by the slots; crops of all sizes share PARSeq batches",
                    "kernel_paths": "conservative (retry after a failed first attempt)" if os.environ.get("TT_BENCH_RETRY") else "default",
+                   "decoder": "26-step AR schedule with per-crop exit at EOS (upstream PARSeq's early exit, which the reference applies per "
+                              "4-crop forward; outputs identical to the full schedule: test_parseq_early_exit_is_output_preserving) + 1 refinement; "
+                              "the CPU baseline / reference arm run the oracle with the same exit per 4-crop chunk",
                    "l2": f"inputs larger than L2: {n * PAGE * PAGE * 3 / 2**20:.0f} MiB of distinct pages per step"},
         "e2e": {"value": e2e, "unit": "pages/s", "h2d_bytes_per_step": r_host["h2d"], "d2h_bytes_per_step": r_host["d2h"],
                 "ms_per_step": r_host["ms"] / args.steps},
@@ -430,11 +440,14 @@ def run_native(args, rank, local_rank, world):
                      "kernel_share_of_step": pm / r_prof["ms"], "serial_ms_per_step": r_prof["ms"] / prof_steps,
                      "note": "per-launch events from an extra timed pass with one execution slot (serial kernels); "
                              "the headline value runs three slots per GPU",
-                     "algorithmic_gflop_per_step": n * (CRAFT_GFLOP_PER_PAGE + WORDS * PARSEQ_GFLOP_PER_CROP)},
+                     # CRAFT + PARSeq encoder + the decoder passes the crops actually took (early exit at EOS)
+                     "algorithmic_gflop_per_step": n * (CRAFT_GFLOP_PER_PAGE + WORDS * PARSEQ_ENC_GFLOP_PER_CROP)
+                                                   + stages.get("parseq_decoder", {}).get("flops", 0.0) / 1e9},
         "stages": stage_lines,
-        "parseq": {"crops_per_s": parseq_cps, "batch": 1024, "frac_tensor": parseq_cps * PARSEQ_GFLOP_PER_CROP / 1e3 / peaks["tf_sustained"],
-                   "note": "configs[2]: 1024 synthetic 32x128 crops, PARSeq-base, 26 AR steps + refinement, host u8 crops in / ids out "
-                           "(wall clock around tt_parseq_forward, this rank)"},
+        "parseq": {"crops_per_s": parseq_cps, "batch": 1024, "frac_tensor": parseq_cps * PARSEQ_ENC_GFLOP_PER_CROP / 1e3 / peaks["tf_sustained"],
+                   "note": "configs[2]: 1024 synthetic 32x128 crops, PARSeq-base, AR pass (<= 26 steps, per-crop exit at EOS) + refinement, "
+                           "host u8 crops in / ids out (wall clock around tt_parseq_forward, this rank); frac_tensor counts the "
+                           "encoder's 5.75 GFLOP per crop only"},
     }
     if rank == 0 and not args.no_configs:
         line["configs"] = other_configs(tb, lib, eng, make_call, torch)
@@ -453,7 +466,7 @@ def run_native(args, rank, local_rank, world):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sec, npg, threads = cpu_pipeline_sample(1)
         line["cpu_baseline"] = {"value": npg / sec, "unit": "pages/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"{npg} page (300 crops), oracle (torch CPU + cv2), torch threads {threads}, "
+                                "sample": f"{npg} page (300 crops), oracle (torch CPU + cv2, upstream AR early exit per 4-crop chunk), torch threads {threads}, "
                                           "PARSeq chunks of 4 on 6 threads (tuatara.cpp:452-475), models pre-loaded"}
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -334,10 +334,16 @@ class PARSeq(nn.Module):
 
     @torch.no_grad()
     def forward(self, images, forced_tokens: torch.Tensor | None = None, taps: dict | None = None):
-        """Fixed 26-step schedule (upstream's early exit only shortens the tensor; positions up
-        to the first EOS are unaffected -- SURVEY App. B).  ``forced_tokens`` (N,25) int64, when
-        given, replaces the argmax feedback so a bf16 implementation can be compared
-        position-by-position without chaotic divergence (teacher forcing; test-only)."""
+        """Fixed 26-step schedule by default (upstream's early exit only shortens the tensor;
+        positions up to the first EOS are unaffected -- SURVEY App. B).  With ``self.early_exit``
+        set, upstream's ``if testing and (tgt_in == self.eos_id).any(dim=-1).all(): break`` is
+        applied as upstream does, per forward() batch -- the reference calls forward() on 4 crops
+        at a time (tuatara.cpp:452-475); bench.py's CPU baseline / reference arm time it that way.
+        The refinement then sees a shorter key sequence; every dropped key is behind an EOS and
+        would be masked, so the returned (N, 26, C) logits are the same.
+        ``forced_tokens`` (N,25) int64, when given, replaces the argmax feedback so a bf16
+        implementation can be compared position-by-position without chaotic divergence (teacher
+        forcing; test-only; no early exit)."""
         bs = images.shape[0]
         num_steps = self.max_label_length + 1
         memory = self.encode(images, taps)
@@ -356,6 +362,9 @@ class PARSeq(nn.Module):
             logits.append(p_i)
             if j < num_steps:
                 tgt_in[:, j] = p_i[:, 0].argmax(-1) if forced_tokens is None else forced_tokens[:, i]
+                if getattr(self, "early_exit", False) and forced_tokens is None and taps is None \
+                        and bool((tgt_in == self.eos_id).any(dim=-1).all()):
+                    break
         logits = torch.cat(logits, dim=1)
         if taps is not None:
             taps["ar_logits"] = logits

@@ -199,6 +199,38 @@ def test_parseq_fused_decoder_matches_unfused(engine, monkeypatch):
         assert same.mean() >= 0.95
 
 
+def test_parseq_early_exit_is_output_preserving(engine, monkeypatch):
+    """Per-crop early exit of the AR loop (a crop leaves once its step produced EOS; upstream PARSeq breaks a batch when
+    every sequence has one, and the reference feeds it 4 crops at a time, tuatara.cpp:452-475) against the full 26-step
+    schedule (TT_DEC_EARLY_EXIT=0): nothing after a crop's first EOS reaches the refinement pass or the string, so
+    the refinement logits and ids are bit-identical at EVERY position, and the AR logits up to the EOS step are too.
+    Sizes: one tile, ragged, two half-batches on two streams (>= 512), and a batch where the lists shrink to nothing."""
+    eos = 0
+    for n, seed in ((128, 11), (77, 12), (1000, 13)):
+        crops = _crops(n + (n & 1), seed=seed)[:n]
+        if n == 1000:
+            crops[500:] = np.random.default_rng(seed).integers(0, 256, crops[500:].shape, dtype=np.uint8)
+        res = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("TT_DEC_EARLY_EXIT", mode)
+            l, i = engine.parseq_forward(crops)
+            monkeypatch.setenv("TT_PARSEQ_AR_LOGITS", "1")
+            la, _ = engine.parseq_forward(crops)
+            monkeypatch.delenv("TT_PARSEQ_AR_LOGITS")
+            res[mode] = (l.copy(), i.copy(), la.copy())
+        monkeypatch.delenv("TT_DEC_EARLY_EXIT")
+        (l1, i1, a1), (l0, i0, a0) = res["1"], res["0"]
+        assert np.array_equal(i1, i0)
+        assert np.array_equal(l1, l0), float(np.abs(l1 - l0).max())
+        # AR pass: step i writes position i; the crop is live up to and including the step whose argmax is EOS
+        ar_tok = a0[..., :95].argmax(-1)                      # [n][26] tokens of the full schedule
+        first = np.where((ar_tok == eos).any(-1), (ar_tok == eos).argmax(-1), ar_tok.shape[1] - 1)
+        live = np.arange(ar_tok.shape[1])[None, :] <= first[:, None]
+        assert np.array_equal(a1[live], a0[live])
+        steps = (first + 1).clip(max=26)
+        print(n, "mean AR steps per crop", float(steps.mean()), "of 26; crops running all 26:", int((steps == 26).sum()))
+
+
 def test_parseq_encoder_layernorm_fusion_matches_unfused(engine, monkeypatch):
     """Encoder with LayerNorm folded into the GEMM epilogues (default) against the standalone LayerNorm kernel
     (TT_ENC_LNFUSE=0), same forced AR context: logits agree to bf16 noise, clear decisions are identical."""

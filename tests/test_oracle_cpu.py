@@ -107,3 +107,23 @@ def test_text_threshold_is_compared_as_float_like_the_reference():
     kept_rows = sorted(int(round(r[0][1])) for r in det)
     assert len(det) == 2 and kept_rows[0] < 12, kept_rows   # the float32(0.7) blob (rows 4..11) and the 1.0 blob survive
     assert float(t) < 0.7   # the whole point: float32(0.7) is below the double 0.7
+
+
+def test_parseq_upstream_early_exit_keeps_the_outputs():
+    """Upstream PARSeq leaves the AR loop once every sequence of the batch has an EOS; the oracle applies it when
+    `early_exit` is set (bench.py's CPU baseline, 4 crops per forward like tuatara.cpp:452-475).  Every key the shorter
+    refinement drops sits behind an EOS and would be masked, so the (N, 26, C) logits and the strings do not change."""
+    from oracle.models import make_parseq
+
+    m = make_parseq("base", 0).eval()
+    x = torch.rand(8, 3, 32, 128, generator=torch.Generator().manual_seed(3))
+    tok = R.Tokenizer()
+    for chunk in (x[:4], x[4:]):
+        m.early_exit = False
+        full = m(chunk)
+        m.early_exit = True
+        short = m(chunk)
+        m.early_exit = False
+        assert short.shape == full.shape
+        assert torch.allclose(short, full, atol=1e-5, rtol=0)
+        assert tok.decode(short) == tok.decode(full)

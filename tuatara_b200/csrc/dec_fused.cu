@@ -45,6 +45,10 @@ struct DenseParams {
   int* tokens;                           // B: [n][L]
   const int* forced;                     // B: [n][L-1] or null
   int n, L, step, n_cls, ncp;
+  // early-exit AR pass: rows are the first *n_act slots of `active` (slot -> crop; logits / tokens are indexed by crop).
+  // Both null: n rows, slot == crop.
+  const int* active;
+  const int* n_act;
   unsigned long long* dbg;               // TT_DEC_DEBUG=1 (development): role cycle counters of CTA 0
 };
 
@@ -92,6 +96,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_dec_dense(const __grid_constant
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
+  const int n_rows = p.n_act ? *p.n_act : p.n;   // live rows of this step (the grid covers all n)
+  if (tile * 128 >= n_rows) return;              // the whole CTA, before any barrier or TMEM allocation
   const long long t_entry = (p.dbg != nullptr && blockIdx.x == 0) ? clock64() : 0;
 
   if (threadIdx.x == 0) {
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dec_dense(const __grid_constant
     const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const long long m = static_cast<long long>(tile) * 128 + r;
-    const bool valid = m < p.n;
+    const bool valid = m < n_rows;   // rows past the live count hold stale activations: computed, never stored
     const uint32_t tl = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t ecnt = 0;
     auto wait_md = [&]() { ptx::mbar_wait(&ctl->md[ecnt & 1], (ecnt >> 1) & 1); ++ecnt; ptx::tc_fence_after(); };
@@ -385,7 +391,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_dec_dense(const __grid_constant
       // ---- head: logits row + greedy token (the halves' maxima meet in smem; the lower half holds the lower classes)
       wait_md();
       {
-        float* lrow = p.logits + (m * p.L + p.step) * p.ncp;
+        const long long crop = (valid && p.active) ? p.active[m] : m;
+        float* lrow = p.logits + (crop * p.L + p.step) * p.ncp;
         float best = -INFINITY;
         int bi = 0;
         const int nb = p.ncp / 32, hb0 = half ? (nb + 1) / 2 : 0, hb1 = half ? nb : (nb + 1) / 2;
@@ -409,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dec_dense(const __grid_constant
           const float ob = xch[r * 2];
           if (ob > best) { best = ob; bi = __float_as_int(xch[r * 2 + 1]); }
           if (valid && p.step + 1 < p.L)
-            p.tokens[m * p.L + p.step + 1] = p.forced ? p.forced[m * (p.L - 1) + p.step] : bi;
+            p.tokens[crop * p.L + p.step + 1] = p.forced ? p.forced[crop * (p.L - 1) + p.step] : bi;
         }
       }
     }
@@ -540,7 +547,7 @@ void dec_dense_free(DecDenseWeights* w) {
 }
 
 cudaError_t dec_dense_a2(const DecDenseWeights& w, const __nv_bfloat16* ab, int n, int step, float* t_scratch,
-                         __nv_bfloat16* q_out, cudaStream_t s) {
+                         __nv_bfloat16* q_out, cudaStream_t s, const int* active, const int* n_act) {
   if (n <= 0) return cudaSuccess;
   if (!w.ready) { set_error("dec_dense_a2: weights not initialised for this width"); return cudaErrorInvalidValue; }
   DenseParams p{};
@@ -549,12 +556,13 @@ cudaError_t dec_dense_a2(const DecDenseWeights& w, const __nv_bfloat16* ab, int 
   p.vec_src = w.vec_a2 + static_cast<size_t>(step) * 4 * w.D;
   p.t_scratch = t_scratch; p.q_out = q_out;
   p.n = n; p.L = w.L; p.step = step; p.n_cls = w.n_cls; p.ncp = w.ncp;
+  p.active = active; p.n_act = n_act;
   if (w.D == 384) return launch_dense<384, 1536, MODE_A2>(p, s);
   return launch_dense<192, 768, MODE_A2>(p, s);
 }
 
 cudaError_t dec_dense_b(const DecDenseWeights& w, const __nv_bfloat16* ab2, int n, int step, const float* t_scratch,
-                        float* logits, int* tokens, const int* forced, cudaStream_t s) {
+                        float* logits, int* tokens, const int* forced, cudaStream_t s, const int* active, const int* n_act) {
   if (n <= 0) return cudaSuccess;
   if (!w.ready) { set_error("dec_dense_b: weights not initialised for this width"); return cudaErrorInvalidValue; }
   DenseParams p{};
@@ -564,6 +572,7 @@ cudaError_t dec_dense_b(const DecDenseWeights& w, const __nv_bfloat16* ab2, int 
   p.t_scratch = const_cast<float*>(t_scratch);
   p.logits = logits; p.tokens = tokens; p.forced = forced;
   p.n = n; p.L = w.L; p.step = step; p.n_cls = w.n_cls; p.ncp = w.ncp;
+  p.active = active; p.n_act = n_act;
   if (w.D == 384) return launch_dense<384, 1536, MODE_B>(p, s);
   return launch_dense<192, 768, MODE_B>(p, s);
 }

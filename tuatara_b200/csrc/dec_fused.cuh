@@ -47,11 +47,14 @@ void dec_dense_free(DecDenseWeights* w);
 size_t dec_dense_scratch_floats(int n, int D);
 
 // ab [n][D] bf16 (self-attention output of step `step`) -> t_scratch (t = posq[step] + out_proj(ab)), q_out [n][D] bf16
+// (active, n_act): the early-exit AR pass's slot -> crop list and its device-side length (nn_kernels.cuh DecoderStep); the
+// rows of ab / q_out / t_scratch are slots, logits and tokens are indexed by crop.  Null: n rows, slot == crop.
 cudaError_t dec_dense_a2(const DecDenseWeights& w, const __nv_bfloat16* ab, int n, int step, float* t_scratch,
-                         __nv_bfloat16* q_out, cudaStream_t s);
+                         __nv_bfloat16* q_out, cudaStream_t s, const int* active = nullptr, const int* n_act = nullptr);
 // ab2 [n][D] bf16 (cross-attention output of step `step`), t_scratch -> logits [n][L][ncp] row `step` (fp32) and the next
 // token: tokens[crop][step + 1] = forced ? forced[crop][step] : argmax over the first n_cls logits (first max wins).
 cudaError_t dec_dense_b(const DecDenseWeights& w, const __nv_bfloat16* ab2, int n, int step, const float* t_scratch,
-                        float* logits, int* tokens, const int* forced, cudaStream_t s);
+                        float* logits, int* tokens, const int* forced, cudaStream_t s, const int* active = nullptr,
+                        const int* n_act = nullptr);
 
 }  // namespace tt

@@ -374,6 +374,12 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
   ARENA_GET(logits, float, static_cast<size_t>(R) * NC);
   ARENA_GET(ids, int, static_cast<size_t>(R));
   ARENA_GET(t_scratch, float, dec_dense_scratch_floats(n, D));
+  ARENA_GET(act, int, static_cast<size_t>(2) * n);       // early exit: two generations of the slot -> crop lists (both halves)
+  ARENA_GET(act_n, int, static_cast<size_t>(2) * L);     // live crops of half h before step i at [h * L + i]
+  const char* ee_env = std::getenv("TT_DEC_EARLY_EXIT");   // read per call: the parity test flips it in-process
+  const bool early = fused && forced == nullptr && !(ee_env && std::atoi(ee_env) == 0);
+  int ar_counts_h[64];
+  double ar_passes = static_cast<double>(n) * L;           // crop-steps of the AR pass
   RUN(tokens_init(tokens, n, L, pd.bos_id, pd.pad_id, s));
   const float* posq = wf.f32("posq");
   const bf* kv_table = w->kv_table;
@@ -399,7 +405,15 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
     // half (128 crops per CTA: 75 CTAs for a 32-page group, latency / L2 bound) overlap the HBM-bound cross attention
     // of the other.  Small batches stay on one stream.
     const int n0 = (n >= 512 && stream2) ? ((n / 2 + 127) / 128) * 128 : n;
-    auto ar_step = [&](int i, int c0, int nc, cudaStream_t hs) -> cudaError_t {
+    // Per-crop early exit: a crop whose step produced EOS leaves the loop (dec_compact keeps the slot -> crop list of the
+    // crops still decoding, its length stays on the device: the grids cover all crops, surplus blocks return at once).
+    // Upstream PARSeq stops a batch once every sequence has an EOS and the reference feeds it 4 crops at a time
+    // (tuatara.cpp:452-475); nothing after a crop's first EOS reaches the refinement pass -- its keys are masked from
+    // there on -- or the decoded string, so the outputs are the ones of the full schedule.  Off under teacher forcing
+    // (the parity tests compare every position) and with TT_DEC_EARLY_EXIT=0.
+    for (int h = 0; h < 2; ++h)
+      for (int i = 0; i < L; ++i) ar_counts_h[h * L + i] = 0;
+    auto ar_step = [&](int i, int c0, int nc, int half, cudaStream_t hs) -> cudaError_t {
       int* tok_h = tokens + static_cast<size_t>(c0) * L;
       bf* ab_h = ab + static_cast<size_t>(c0) * D;
       bf* qc_h = qc + static_cast<size_t>(c0) * D;
@@ -407,24 +421,38 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
       float* la_h = logits_ar + static_cast<size_t>(c0) * L * NC;
       const int* forced_h = forced ? forced + static_cast<size_t>(c0) * (L - 1) : nullptr;
       const bf* mkv_h = mem_kv + static_cast<size_t>(c0) * 128 * 2 * D;
+      // lists hold crop indices relative to the half; step 0 works on all of them (no list)
+      int* const cnt = act_n + half * L;
+      const int* cur = (early && i > 0) ? act + static_cast<size_t>(i & 1) * n + c0 : nullptr;
+      const int* cur_n = (early && i > 0) ? cnt + i : nullptr;
       DecoderStep st{nc, D, pd.dec_heads, L, i, 1, 0};
+      st.active = cur; st.n_act = cur_n;
       RUN(dec_self_attn(st, w->q_sa_table, w->sc_table, kv_table, tok_h, pd.eos_id, pd.n_tok, ab_h, hs));
-      RUN(dec_dense_a2(w->dd, ab_h, nc, i, ts_h, qc_h, hs));
+      RUN(dec_dense_a2(w->dd, ab_h, nc, i, ts_h, qc_h, hs, cur, cur_n));
       RUN(dec_cross_attn(st, qc_h, mkv_h, ab_h, hs));
-      RUN(dec_dense_b(w->dd, ab_h, nc, i, ts_h, la_h, tok_h, forced_h, hs));
+      RUN(dec_dense_b(w->dd, ab_h, nc, i, ts_h, la_h, tok_h, forced_h, hs, cur, cur_n));
+      if (early && i + 1 < L)
+        RUN(dec_compact(cur, cur_n, nc, tok_h, L, i + 1, pd.eos_id, act + static_cast<size_t>((i + 1) & 1) * n + c0, cnt + i + 1, hs));
       return cudaSuccess;
     };
     if (n0 < n) {
       TT_CUDA_TRY(cudaEventRecord(ev_fork, s));
       TT_CUDA_TRY(cudaStreamWaitEvent(stream2, ev_fork, 0));
       for (int i = 0; i < L; ++i) {   // launches interleaved so that neither stream's queue runs dry
-        RUN(ar_step(i, 0, n0, s));
-        RUN(ar_step(i, n0, n - n0, stream2));
+        RUN(ar_step(i, 0, n0, 0, s));
+        RUN(ar_step(i, n0, n - n0, 1, stream2));
       }
       TT_CUDA_TRY(cudaEventRecord(ev_join, stream2));
       TT_CUDA_TRY(cudaStreamWaitEvent(s, ev_join, 0));
     } else {
-      for (int i = 0; i < L; ++i) RUN(ar_step(i, 0, n, s));
+      for (int i = 0; i < L; ++i) RUN(ar_step(i, 0, n, 0, s));
+    }
+    if (early && prof_enabled()) {   // the stage's algorithmic work is what the live crops did: read the counts back (profiling passes only)
+      TT_CUDA_TRY(cudaMemcpyAsync(ar_counts_h, act_n, sizeof(int) * 2 * L, cudaMemcpyDeviceToHost, s));
+      TT_CUDA_TRY(stream_sync(s));
+      ar_passes = static_cast<double>(n);   // step 0: every crop
+      for (int h = 0; h < (n0 < n ? 2 : 1); ++h)
+        for (int i = 1; i < L; ++i) ar_passes += ar_counts_h[h * L + i];
     }
   } else {
     for (int i = 0; i < L; ++i) {
@@ -438,8 +466,12 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
   DecoderStep st{n, D, pd.dec_heads, L, 0, L, 1};
   RUN(stream_tail(st, R, logits, NC));
   RUN(argmax_rows(logits, R, pd.n_cls, NC, ids, 1, nullptr, 0, nullptr, 0, s));
-  // decoder: 2 x 0.153 GMAC per crop; its floor is the 27 reads of the crop's memory K|V (128 x 768 bf16)
-  stage_end(s, "parseq_decoder", 0.306e9 * n, 27.0 * n * 128 * 768 * 2);
+  // decoder: 2 x 0.153 GMAC per crop over L + 1 passes; its floor is one read of the crop's memory K|V (128 x 768 bf16) per
+  // pass the crop takes part in: L AR steps (fewer with the early exit) + the refinement
+  {
+    const double passes = ar_passes + n;
+    stage_end(s, "parseq_decoder", 0.306e9 / (L + 1) * passes, passes * 128 * 768 * 2);
+  }
   // test hook (tests/test_models_gpu.py): hand back the AR pass's logits instead of the refinement's
   const char* ar_env = std::getenv("TT_PARSEQ_AR_LOGITS");
   *logits_out = (ar_env && std::atoi(ar_env) != 0) ? logits_ar : logits;

@@ -630,11 +630,13 @@ template <int HEADS>
 __global__ void __launch_bounds__(256) k_dec_self_attn_ar(int n, int D, int L, int step, int n_tok,
                                                           const float* __restrict__ sc_table,
                                                           const __nv_bfloat16* __restrict__ kv_table,
-                                                          const int* __restrict__ tokens, __nv_bfloat16* __restrict__ out) {
+                                                          const int* __restrict__ tokens, __nv_bfloat16* __restrict__ out,
+                                                          const int* __restrict__ active, const int* __restrict__ n_act) {
   __shared__ float s_p[8][HEADS][32];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int crop = blockIdx.x * 8 + wib;
-  if (crop >= n) return;
+  const int slot = blockIdx.x * 8 + wib;
+  if (slot >= (n_act ? *n_act : n)) return;
+  const int crop = active ? active[slot] : slot;   // tokens by crop, the output row by slot
   const int nkeys = step + 1;
   const int tok = lane < nkeys ? tokens[crop * L + lane] : 0;
   float sc[HEADS];
@@ -698,7 +700,7 @@ __global__ void __launch_bounds__(256) k_dec_self_attn_ar(int n, int D, int L, i
       }
     }
   }
-  __nv_bfloat16* orow = out + static_cast<long long>(crop) * D;
+  __nv_bfloat16* orow = out + static_cast<long long>(slot) * D;
   if (one) st8(orow + lane * 8, pack8(a0));
   if (two) st8(orow + (lane + 32) * 8, pack8(a1));
 }
@@ -715,9 +717,14 @@ __global__ void __launch_bounds__(kD) k_dec_cross_attn(DecoderStep st, const __n
   constexpr int kHeads = kD / 32, kKeys = 128, kWarps = kHeads, kUnits = kD / 8;  // 48 (base) / 24 (tiny) 16-byte units per K row
   __shared__ float s_sc[kHeads][kKeys];         // scores, then probabilities
   __shared__ float s_part[kWarps][kD];          // per-warp partial outputs
-  const int pi = blockIdx.x, crop = blockIdx.y;
+  const int pi = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(crop) * st.np + pi;
+  // early-exit AR pass: the grid covers at most all crops, the blocks walk the active slots (q / out rows by slot, the
+  // memory K|V by crop); without a list every block has exactly its own crop
+  const int n_slots = st.n_act ? *st.n_act : st.n_crops;
+  for (int slot = blockIdx.y; slot < n_slots; slot += gridDim.y) {
+  const int crop = st.active ? st.active[slot] : slot;
+  const long long row = static_cast<long long>(slot) * st.np + pi;
   const __nv_bfloat16* kvb = mem_kv + static_cast<long long>(crop) * kKeys * 2 * kD;
   // q slices for the (up to) two units this lane covers: unit lane, unit 32 + lane (lane < 16)
   float qa[8], qb[8];
@@ -792,6 +799,8 @@ __global__ void __launch_bounds__(kD) k_dec_cross_attn(DecoderStep st, const __n
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) acc += s_part[w][d];
     out[row * kD + d] = __float2bfloat16(acc);
+  }
+  __syncthreads();   // s_sc / s_part are reused by the next slot
   }
 }
 
@@ -1103,8 +1112,8 @@ cudaError_t dec_self_attn(const DecoderStep& st, const float* q_table, const flo
   if (st.D != st.heads * 32 || st.L > 32) { set_error("dec_self_attn: head dim must be 32, L <= 32"); return cudaErrorInvalidValue; }
   if (!st.refine && st.np == 1 && sc_table != nullptr && (st.heads == 12 || st.heads == 6) && st.D <= 512) {
     const int grid = (st.n_crops + 7) / 8;
-    if (st.heads == 12) k_dec_self_attn_ar<12><<<grid, 256, 0, s>>>(st.n_crops, st.D, st.L, st.p0, n_tok, sc_table, kv, tokens, out);
-    else k_dec_self_attn_ar<6><<<grid, 256, 0, s>>>(st.n_crops, st.D, st.L, st.p0, n_tok, sc_table, kv, tokens, out);
+    if (st.heads == 12) k_dec_self_attn_ar<12><<<grid, 256, 0, s>>>(st.n_crops, st.D, st.L, st.p0, n_tok, sc_table, kv, tokens, out, st.active, st.n_act);
+    else k_dec_self_attn_ar<6><<<grid, 256, 0, s>>>(st.n_crops, st.D, st.L, st.p0, n_tok, sc_table, kv, tokens, out, st.active, st.n_act);
     TT_LAUNCH_CHECK();
     return cudaSuccess;
   }
@@ -1133,8 +1142,56 @@ cudaError_t dec_cross_attn(const DecoderStep& st, const __nv_bfloat16* q, const 
     TT_LAUNCH_CHECK();
     return cudaSuccess;
   }
-  if (st.D == 384) k_dec_cross_attn<384><<<dim3(st.np, st.n_crops), 384, 0, s>>>(st, q, mem_kv, out);
-  else k_dec_cross_attn<192><<<dim3(st.np, st.n_crops), 192, 0, s>>>(st, q, mem_kv, out);
+  // with an active list the live count is only known on the device: a bounded grid whose blocks stride over the slots
+  const int gy = st.n_act ? std::min(st.n_crops, 8 * 148) : st.n_crops;   // 8 blocks per B200 SM
+  if (st.D == 384) k_dec_cross_attn<384><<<dim3(st.np, gy), 384, 0, s>>>(st, q, mem_kv, out);
+  else k_dec_cross_attn<192><<<dim3(st.np, gy), 192, 0, s>>>(st, q, mem_kv, out);
+  TT_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+// Order-preserving compaction of the AR pass's active list (one block: a half-batch is a few thousand crops).
+__global__ void __launch_bounds__(1024) k_dec_compact(const int* __restrict__ active_in, const int* __restrict__ n_in, int n,
+                                                      const int* __restrict__ tokens, int L, int pos, int eos_id,
+                                                      int* __restrict__ active_out, int* __restrict__ n_out) {
+  __shared__ int s_off[32];    // exclusive offsets of the 32 warps inside a 1024-slot chunk
+  __shared__ int s_total;      // kept slots of the chunk
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_slots = n_in ? *n_in : n;
+  int base = 0;                // kept slots of the chunks before this one (the same in every thread)
+  for (int s0 = 0; s0 < n_slots; s0 += 1024) {
+    const int slot = s0 + threadIdx.x;
+    int crop = 0;
+    bool keep = false;
+    if (slot < n_slots) {
+      crop = active_in ? active_in[slot] : slot;
+      keep = tokens[static_cast<long long>(crop) * L + pos] != eos_id;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_off[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      const int v = s_off[lane];
+      int incl = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      s_off[lane] = incl - v;
+      if (lane == 31) s_total = incl;
+    }
+    __syncthreads();
+    if (keep) active_out[base + s_off[warp] + __popc(m & ((1u << lane) - 1u))] = crop;
+    base += s_total;
+    __syncthreads();           // s_off / s_total are rewritten by the next chunk
+  }
+  if (threadIdx.x == 0) *n_out = base;
+}
+
+cudaError_t dec_compact(const int* active_in, const int* n_in, int n, const int* tokens, int L, int pos, int eos_id,
+                        int* active_out, int* n_out, cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  k_dec_compact<<<1, 1024, 0, s>>>(active_in, n_in, n, tokens, L, pos, eos_id, active_out, n_out);
   TT_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -36,6 +36,11 @@ struct DecoderStep {
   int L;            // 26 positions
   int p0, np;       // query positions [p0, p0+np) handled by this pass
   int refine;       // 0: AR causal mask (keys 0..p); 1: cloze mask + key padding after the first EOS
+  // AR pass with per-crop early exit (nets.cpp): the step works on the first *n_act entries of `active` (slot -> crop).
+  // Per-step activations (q, attention outputs) are indexed by slot; tokens, memory K|V and logits by crop.
+  // Both null: every crop is active and slot == crop.
+  const int* active = nullptr;
+  const int* n_act = nullptr;
 };
 // content embedding of position `pos` (bos at 0, else pos_queries[pos-1] + sqrt(D)*E[tok]) -> LN_c -> bf16 [n][D]
 cudaError_t dec_context(const int* tokens, const float* embed, const float* posq, const float* g, const float* b,
@@ -59,6 +64,12 @@ cudaError_t argmax_rows(const float* logits, int rows, int n_cls, int ld, int* i
                         int* next_tokens, int next_stride, const int* forced, int forced_stride, cudaStream_t s);
 // u8 crops [n][32][128][3] -> bf16 patch rows [n*128][96] (raw 0..255), k = c*32 + (y%4)*8 + x%8
 cudaError_t tokens_init(int* tokens, int n, int L, int bos, int pad, cudaStream_t s);
+// AR early exit: the crops of (active_in, *n_in) -- null: all n crops -- whose token at position `pos` is not EOS, in the
+// same order -> active_out, *n_out.  A crop that has produced EOS leaves the AR loop: upstream PARSeq stops a batch when
+// every sequence has one, and nothing after a crop's first EOS reaches the refinement pass (its keys are masked from
+// there on) or the decoded string.
+cudaError_t dec_compact(const int* active_in, const int* n_in, int n, const int* tokens, int L, int pos, int eos_id,
+                        int* active_out, int* n_out, cudaStream_t s);
 // x fp32 [n] -> hi = bf16(x), lo = bf16(x - hi)  (split residual stream, gemm_tc.cuh RES_SPLIT)
 cudaError_t split_f32(const float* x, long long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t s);
 cudaError_t patchify_u8(const uint8_t* crops, int n, __nv_bfloat16* out, cudaStream_t s);
