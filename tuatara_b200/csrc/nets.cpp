@@ -249,6 +249,7 @@ size_t DeviceCtx::parseq_bytes(int n) const {
   const size_t R = static_cast<size_t>(n) * pd.L;
   b += R * 4 + R * D * (4 + 2 + 2 + 2) + R * pd.mlp * 2 + 2 * R * pd.n_cls_pad * 4 + 2 * R * 4;
   b += dec_dense_scratch_floats(n, pd.D) * 4;
+  b += (static_cast<size_t>(2) * n + 2 * pd.L) * 4;   // early exit: slot -> crop lists and their lengths
   return b + (1u << 20);
 }
 
