@@ -12,10 +12,13 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm
   -o gpurun_out/prof_lnpair_proj_fc1_$TAG python tools/ln_probe.py 384 1536 2 > gpurun_out/ncu_lnpair1_$TAG.log 2>&1; echo "ln pair proj+fc1 rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 4 -c 2 -f \
   -o gpurun_out/prof_lnpair_fc2_qkv_$TAG python tools/ln_probe.py 1536 1152 0 > gpurun_out/ncu_lnpair2_$TAG.log 2>&1; echo "ln pair fc2+qkv rc=$?"
+# decoder kernels at full occupancy: the full 26-step schedule (with the early exit the launches past step ~4 are nearly empty)
 for k in k_dec_dense k_dec_cross_attn; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 60 -c 2 -f \
+  TT_DEC_EARLY_EXIT=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 60 -c 2 -f \
     -o gpurun_out/prof_${k}_$TAG python tools/dec_bench.py 9600 > gpurun_out/ncu_${k}_$TAG.log 2>&1; echo "$k rc=$?"
 done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_attn_enc -s 14 -c 1 -f \
+    -o gpurun_out/prof_k_attn_enc_$TAG python tools/dec_bench.py 9600 > gpurun_out/ncu_k_attn_enc_$TAG.log 2>&1; echo "k_attn_enc rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_conv1_1 -s 2 -c 1 -f \
     -o gpurun_out/prof_conv1_1_$TAG python tools/stage_bench.py 8 quick > gpurun_out/ncu_conv1_1_$TAG.log 2>&1
 echo "full capture conv1_1 rc=$?"
