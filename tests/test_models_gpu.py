@@ -249,6 +249,27 @@ def test_parseq_encoder_layernorm_fusion_matches_unfused(engine, monkeypatch):
     assert (idf[clear] == idu[clear]).all()
 
 
+def test_parseq_encoder_mlp_fusion_matches_unfused(engine, monkeypatch):
+    """Encoder with the MLP block as one kernel (enc_mlp.cu, default) against the fc1 / fc2 GEMM launches
+    (TT_ENC_MLPFUSE=0), same forced AR context: logits agree to bf16 noise, clear decisions are identical.  Sizes: an odd
+    number of 128-row tiles per pair schedule (77 crops) and more tiles than CTA pairs (300 crops)."""
+    for n, seed in ((77, 21), (300, 22)):
+        crops = _crops(n + (n & 1), seed=seed)[:n]
+        _, id0 = engine.parseq_forward(crops)
+        forced = np.ascontiguousarray(id0[:, :25]).astype(np.int32)
+        lf, idf = engine.parseq_forward(crops, forced)
+        monkeypatch.setenv("TT_ENC_MLPFUSE", "0")
+        lu, idu = engine.parseq_forward(crops, forced)
+        monkeypatch.delenv("TT_ENC_MLPFUSE")
+        err = _rel_l2(lf, lu)
+        top2 = np.sort(lu, -1)[..., -2:]
+        clear = (top2[..., 1] - top2[..., 0]) > 0.5
+        print(n, "fused-MLP vs two-GEMM encoder: logits rel-L2", err, "ids equal", float((idf == idu).mean()))
+        assert np.isfinite(lf).all()
+        assert 0 < err <= 1e-2, err
+        assert (idf[clear] == idu[clear]).all()
+
+
 def test_parseq_tiny_variant(oracle_models):
     """PARSeq-tiny (embed 192, 3 encoder / 6 decoder heads, MLP 768: the other variant the HuggingFace checkpoint may be,
     /root/reference/.gitignore:1): dims come from the weight file's meta tensor; logits against the fp32 oracle under

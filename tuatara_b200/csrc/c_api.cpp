@@ -9,6 +9,7 @@
 
 #include "common.h"
 #include "detect.h"
+#include "enc_mlp.cuh"
 #include "engine.h"
 #include "gemm_tc.cuh"
 #include "geometry.h"
@@ -342,6 +343,17 @@ int tt_linear_ln_pair_dev(const void* A, int M, int K1, const void* W1, const fl
       if (linear_forward(l, e, s) != cudaSuccess) return 1;
     }
     return 0;
+  });
+}
+
+int tt_enc_mlp_dev(void* x_hi, void* x_lo, float* stats, long long M, const void* W1f, const float* c0, const float* c1,
+                   const void* W2, const float* b2, float eps, void* stream) {
+  return guarded([&]() -> int {
+    EncMlpWeights w;
+    w.w1 = static_cast<const __nv_bfloat16*>(W1f); w.c0 = c0; w.c1 = c1;
+    w.w2 = static_cast<const __nv_bfloat16*>(W2); w.b2 = b2;
+    return enc_mlp_forward(w, static_cast<__nv_bfloat16*>(x_hi), static_cast<__nv_bfloat16*>(x_lo), stats, 2, M, 384, 1536, eps,
+                           static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : 1;
   });
 }
 

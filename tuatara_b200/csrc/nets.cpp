@@ -12,6 +12,7 @@
 
 #include "common.h"
 #include "dec_fused.cuh"
+#include "enc_mlp.cuh"
 #include "engine.h"
 #include "gemm_tc.cuh"
 #include "nn_kernels.cuh"
@@ -288,6 +289,10 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
   // weights.py; TT_ENC_LNFUSE=0 keeps the fp32 stream and the standalone LayerNorm kernel (A/B runs, parity test).
   const char* lnf_env = std::getenv("TT_ENC_LNFUSE");
   const bool lnf = !(lnf_env && std::atoi(lnf_env) == 0) && wf.has("b0.qkv.wf") && wf.has("dec.ca.kvf.wf");
+  // fc1 + GELU + fc2 + residual as one kernel (enc_mlp.cu; PARSeq-base dims, split stream): the hidden activations stay
+  // on the SM.  TT_ENC_MLPFUSE=0 keeps the two GEMM launches (A/B runs, parity test); PARSeq-tiny always takes them.
+  const char* mf_env = std::getenv("TT_ENC_MLPFUSE");   // read per call: the parity test flips it in-process
+  const bool mlp_fuse = lnf && !(mf_env && std::atoi(mf_env) == 0) && enc_mlp_supported(D, pd.mlp);
   ARENA_GET(x, float, Mc * D);       // fp32 residual stream (unfused) / the lo half of the split stream (fused; first half of the buffer)
   ARENA_GET(h, bf, Mc * D);          // LayerNorm output (unfused) / the hi half of the split stream = bf16(x) (fused)
   bf* const x_lo = reinterpret_cast<bf*>(x);
@@ -342,6 +347,14 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
       RUN(ln_gemm(p + "qkv", Mi, 3 * D, ACT_NONE, qkv));
       RUN(attention_enc(qkv, att, nc, D, pd.enc_heads, s));
       RUN(res_gemm(att, D, Mi, D, wf.bf(p + "proj.w"), wf.f32(p + "proj.b"), nullptr, 0));
+      if (mlp_fuse && ln_parts == 2) {
+        // fc1 -> GELU -> fc2 -> residual in one kernel: the hidden activations stay on the SM (enc_mlp.cu)
+        EncMlpWeights mw;
+        mw.w1 = wf.bf(p + "fc1.wf"); mw.c0 = wf.f32(p + "fc1.c0"); mw.c1 = wf.f32(p + "fc1.c1");
+        mw.w2 = wf.bf(p + "fc2.w"); mw.b2 = wf.f32(p + "fc2.b");
+        RUN(enc_mlp_forward(mw, h, x_lo, lnstats, ln_parts, Mi, D, pd.mlp, 1e-6f, s));
+        continue;
+      }
       if (!lnf) RUN(layernorm(x, Mi, D, wf.f32(p + "ln2.g"), wf.f32(p + "ln2.b"), 1e-6f, h, nullptr, 0, s));
       RUN(ln_gemm(p + "fc1", Mi, pd.mlp, ACT_GELU, hid));
       RUN(res_gemm(hid, pd.mlp, Mi, pd.mlp, wf.bf(p + "fc2.w"), wf.f32(p + "fc2.b"), nullptr, 0));
