@@ -433,7 +433,7 @@ def run_native(args, rank, local_rank, world):
                 "ms_per_step": r_host["ms"] / args.steps},
         "gpu_launches": int(r_dev["launches"]),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv)",
+        "roofline": {"bound": "tensor", "kernel": "the tcgen05 GEMM kernels: gemm_tc_kernel (GEMM / implicit-GEMM conv) + k_enc_mlp (fused encoder MLP block)",
                      "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tf_sustained"], "traffic": gemm_traffic(), "peak_source": peaks["source"],
                      "launches": int(pl), "kernel_ms_per_step": pm / prof_steps,

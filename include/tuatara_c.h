@@ -191,13 +191,15 @@ TT_API int tt_linear_dev(const void* A, int lda, int M, int K, const void* W, in
 TT_API int tt_linear_ln_pair_dev(const void* A, int M, int K1, const void* W1, const float* b1, int D, void* x_hi, void* x_lo,
                           float* stats, const void* W2f, const float* c0, const float* c1, int N2, int act, float eps,
                           void* out, void* stream);
-/* Kernel test of the fused MLP block of the PARSeq-base encoder (timm Block: x += fc2(GELU(fc1(LN2(x)))), reached by the
- * reference through TorchScript at tuatara.cpp:307): one kernel, the hidden activations never leave the SM.  The residual
- * stream is the split pair of tt_linear_ln_pair_dev (bf16 [M][384] each, updated in place); stats fp32 [M][4]: on entry
- * two partial (sum x, sum x^2) pairs per row, on return the two partials of the new x; W1f = fc1 * gamma bf16 [1536][384],
- * c0 / c1 as above, W2 bf16 [384][1536], b2 fp32 [384].  All device pointers. */
-TT_API int tt_enc_mlp_dev(void* x_hi, void* x_lo, float* stats, long long M, const void* W1f, const float* c0, const float* c1,
-                   const void* W2, const float* b2, float eps, void* stream);
+/* Kernel test of the fused second half of a PARSeq-base encoder block (timm Block, reached by the reference through
+ * TorchScript at tuatara.cpp:307):  x += att Wp^T + bp  (the attention output projection; skipped when att is NULL), then
+ * x += fc2(GELU(fc1(LN2(x)))) -- one kernel, neither x1 nor the hidden activations leave the SM.  The residual stream is the
+ * split pair of tt_linear_ln_pair_dev (bf16 [M][384] each, updated in place); stats fp32 [M][4]: with att == NULL two
+ * partial (sum x, sum x^2) pairs per row on entry; on return the two partials of the new x.  att bf16 [M][384], Wp bf16
+ * [384][384], bp fp32 [384]; W1f = fc1 * gamma bf16 [1536][384], c0 / c1 as above, W2 bf16 [384][1536], b2 fp32 [384].
+ * All device pointers. */
+TT_API int tt_enc_mlp_dev(void* x_hi, void* x_lo, float* stats, long long M, const void* att, const void* Wp, const float* bp,
+                   const void* W1f, const float* c0, const float* c1, const void* W2, const float* b2, float eps, void* stream);
 /* NHWC bf16 stride-1 "same" convolution as implicit GEMM; src1 may be NULL (else channel concat).
  * weight bf16 [Cout][taps][C0+C1]; out bf16 [batch][H][W][Cout]. */
 TT_API int tt_conv_dev(const void* src0, int C0, const void* src1, int C1, int batch, int H, int W, int taps, int dil,

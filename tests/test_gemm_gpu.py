@@ -226,17 +226,19 @@ def test_linear_layernorm_fused_pair(native_lib, M, K1, N2, act):
     assert float(err) <= 6e-3, float(err)
 
 
+@pytest.mark.parametrize("proj", [False, True])
 @pytest.mark.parametrize("M", [128, 384, 2432, 38400])
-def test_fused_encoder_mlp_kernel(native_lib, M):
-    """k_enc_mlp (enc_mlp.cu): x += fc2(GELU(fc1(LN(x)))) of a PARSeq-base encoder block in one kernel -- CTA pairs,
-    the hidden activations go from registers to the smem tile fc2 reads, the residual stream stays the split
-    (hi, lo) bf16 pair, the rows' LayerNorm sums are emitted for the next layer.  Reference: fp32 torch.
-    Sizes: one half-filled pair tile, an odd number of 128-row tiles (the pair's second CTA past the end), more tiles than
-    CTA pairs (several tiles per pair, ragged), and a batch of 300 crops."""
+def test_fused_encoder_mlp_kernel(native_lib, M, proj):
+    """k_enc_mlp (enc_mlp.cu): the second half of a PARSeq-base encoder block in one kernel -- optionally the attention
+    output projection (x += att Wp^T + bp, the residual rows added into the TMEM accumulator through an identity
+    operand), then x += fc2(GELU(fc1(LN(x)))): CTA pairs, the hidden activations go from registers to the smem tile fc2
+    reads, the residual stream stays the split (hi, lo) bf16 pair, the rows' LayerNorm sums are emitted for the next layer.
+    Reference: fp32 torch.  Sizes: one half-filled pair tile, an odd number of 128-row tiles (the pair's second CTA past
+    the end), more tiles than CTA pairs (several tiles per pair, ragged), and a batch of 300 crops."""
     from tuatara_b200._native import check
 
     D, H = 384, 1536
-    g = torch.Generator(device="cpu").manual_seed(M)
+    g = torch.Generator(device="cpu").manual_seed(M + int(proj))
     X0 = (torch.randn(M, D, generator=g) * 1.5 + 0.3).float().cuda()
     gamma = (1.0 + 0.2 * (torch.rand(D, generator=g) - 0.5)).cuda()
     beta = (0.05 * torch.randn(D, generator=g)).cuda()
@@ -244,6 +246,9 @@ def test_fused_encoder_mlp_kernel(native_lib, M):
     b1 = (torch.randn(H, generator=g) * 0.02).cuda()
     W2 = (torch.randn(D, H, generator=g) * 0.03).to(torch.bfloat16).cuda()
     b2 = (torch.randn(D, generator=g) * 0.1).float().cuda()
+    att = (torch.randn(M, D, generator=g) * 0.7).to(torch.bfloat16).cuda()
+    Wp = (torch.randn(D, D, generator=g) * 0.05).to(torch.bfloat16).cuda()
+    bp = (torch.randn(D, generator=g) * 0.1).float().cuda()
     W1f = (W1 * gamma[None, :]).to(torch.bfloat16)
     c1 = W1f.double().sum(1).float()
     c0 = (b1.double() + W1.double() @ beta.double()).float()
@@ -251,18 +256,21 @@ def test_fused_encoder_mlp_kernel(native_lib, M):
     XL = (X0 - XH.float()).to(torch.bfloat16)
     x_in = XH.float() + XL.float()
     stats = torch.zeros(M, 4, device="cuda")
-    stats[:, 0] = x_in[:, :192].sum(1); stats[:, 1] = (x_in[:, :192] ** 2).sum(1)
-    stats[:, 2] = x_in[:, 192:].sum(1); stats[:, 3] = (x_in[:, 192:] ** 2).sum(1)
-    check(native_lib.tt_enc_mlp_dev(XH.data_ptr(), XL.data_ptr(), stats.data_ptr(), M, W1f.data_ptr(), c0.data_ptr(), c1.data_ptr(),
-                                    W2.data_ptr(), b2.data_ptr(), 1e-6, None), "tt_enc_mlp_dev")
+    if not proj:   # with the projection the kernel forms the LayerNorm sums of x1 itself
+        stats[:, 0] = x_in[:, :192].sum(1); stats[:, 1] = (x_in[:, :192] ** 2).sum(1)
+        stats[:, 2] = x_in[:, 192:].sum(1); stats[:, 3] = (x_in[:, 192:] ** 2).sum(1)
+    check(native_lib.tt_enc_mlp_dev(XH.data_ptr(), XL.data_ptr(), stats.data_ptr(), M, att.data_ptr() if proj else None,
+                                    Wp.data_ptr() if proj else None, bp.data_ptr() if proj else None, W1f.data_ptr(), c0.data_ptr(),
+                                    c1.data_ptr(), W2.data_ptr(), b2.data_ptr(), 1e-6, None), "tt_enc_mlp_dev")
     torch.cuda.synchronize()
     X = XH.float() + XL.float()
-    h = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x_in, (D,), gamma, beta, 1e-6) @ W1.t() + b1)
-    x_ref = x_in + h @ W2.float().t() + b2
+    x1 = x_in + (att.float() @ Wp.float().t() + bp if proj else 0.0)
+    h = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x1, (D,), gamma, beta, 1e-6) @ W1.t() + b1)
+    x_ref = x1 + h @ W2.float().t() + b2
     assert torch.isfinite(X).all()
     err = float((X - x_ref).norm() / x_ref.norm())
     upd = float(((X - x_in) - (x_ref - x_in)).norm() / (x_ref - x_in).norm())
-    print(f"M={M}: fused MLP x' rel-L2 {err:.2e}, update rel-L2 {upd:.2e}")
+    print(f"M={M} proj={proj}: fused block x' rel-L2 {err:.2e}, update rel-L2 {upd:.2e}")
     assert err <= 2e-3 and upd <= 8e-3, (err, upd)
     assert bool(((XH.float() - X).abs() <= X.abs() * 2.0 ** -8 + 1e-30).all()), "hi = bf16(x)"
     # the emitted partial sums are those of the new rows

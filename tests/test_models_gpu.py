@@ -257,17 +257,21 @@ def test_parseq_encoder_mlp_fusion_matches_unfused(engine, monkeypatch):
         crops = _crops(n + (n & 1), seed=seed)[:n]
         _, id0 = engine.parseq_forward(crops)
         forced = np.ascontiguousarray(id0[:, :25]).astype(np.int32)
-        lf, idf = engine.parseq_forward(crops, forced)
+        lf, idf = engine.parseq_forward(crops, forced)          # default: proj + MLP in one kernel
+        monkeypatch.setenv("TT_ENC_PROJFUSE", "0")
+        lm, idm = engine.parseq_forward(crops, forced)          # proj as a GEMM launch, the MLP fused
+        monkeypatch.delenv("TT_ENC_PROJFUSE")
         monkeypatch.setenv("TT_ENC_MLPFUSE", "0")
-        lu, idu = engine.parseq_forward(crops, forced)
+        lu, idu = engine.parseq_forward(crops, forced)          # proj, fc1, fc2 as GEMM launches
         monkeypatch.delenv("TT_ENC_MLPFUSE")
-        err = _rel_l2(lf, lu)
         top2 = np.sort(lu, -1)[..., -2:]
         clear = (top2[..., 1] - top2[..., 0]) > 0.5
-        print(n, "fused-MLP vs two-GEMM encoder: logits rel-L2", err, "ids equal", float((idf == idu).mean()))
-        assert np.isfinite(lf).all()
-        assert 0 < err <= 1e-2, err
-        assert (idf[clear] == idu[clear]).all()
+        for name, l, i in (("proj+MLP kernel", lf, idf), ("MLP kernel", lm, idm)):
+            err = _rel_l2(l, lu)
+            print(n, name, "vs GEMM launches: logits rel-L2", err, "ids equal", float((i == idu).mean()))
+            assert np.isfinite(l).all()
+            assert 0 < err <= 1e-2, err
+            assert (i[clear] == idu[clear]).all()
 
 
 def test_parseq_tiny_variant(oracle_models):

@@ -23,7 +23,9 @@ def main():
         forced = np.ascontiguousarray(i0[:, :25]).astype(np.int32)
         l0, i0 = eng.parseq_forward(crops, forced)
         os.environ["TT_ENC_MLPFUSE"] = "1"
+        os.environ["TT_ENC_PROJFUSE"] = os.environ.get("PROBE_PROJ", "0")
         l1, i1 = eng.parseq_forward(crops, forced)
+        os.environ["TT_ENC_PROJFUSE"] = "0"
         os.environ["TT_ENC_MLPFUSE"] = "0"
         err = float(np.linalg.norm(l1.astype(np.float64) - l0) / np.linalg.norm(l0.astype(np.float64)))
         print(f"n={n}: finite {bool(np.isfinite(l1).all())} rel-L2 {err:.3e} ids equal {float((i0 == i1).mean()):.4f}", flush=True)

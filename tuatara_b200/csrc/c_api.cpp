@@ -346,14 +346,16 @@ int tt_linear_ln_pair_dev(const void* A, int M, int K1, const void* W1, const fl
   });
 }
 
-int tt_enc_mlp_dev(void* x_hi, void* x_lo, float* stats, long long M, const void* W1f, const float* c0, const float* c1,
-                   const void* W2, const float* b2, float eps, void* stream) {
+int tt_enc_mlp_dev(void* x_hi, void* x_lo, float* stats, long long M, const void* att, const void* Wp, const float* bp,
+                   const void* W1f, const float* c0, const float* c1, const void* W2, const float* b2, float eps, void* stream) {
   return guarded([&]() -> int {
     EncMlpWeights w;
     w.w1 = static_cast<const __nv_bfloat16*>(W1f); w.c0 = c0; w.c1 = c1;
     w.w2 = static_cast<const __nv_bfloat16*>(W2); w.b2 = b2;
+    EncProj pj;
+    pj.att = static_cast<const __nv_bfloat16*>(att); pj.wp = static_cast<const __nv_bfloat16*>(Wp); pj.bp = bp;
     return enc_mlp_forward(w, static_cast<__nv_bfloat16*>(x_hi), static_cast<__nv_bfloat16*>(x_lo), stats, 2, M, 384, 1536, eps,
-                           static_cast<cudaStream_t>(stream)) == cudaSuccess ? 0 : 1;
+                           static_cast<cudaStream_t>(stream), att ? &pj : nullptr) == cudaSuccess ? 0 : 1;
   });
 }
 

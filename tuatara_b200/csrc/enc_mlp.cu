@@ -46,12 +46,17 @@ constexpr int kEpiWarps = 8;
 constexpr int kRowThreads = 32 * kEpiWarps;
 constexpr int kStoreWarp = 2 + kEpiWarps;   // warp 10: hands finished output blocks to TMA stores
 constexpr int kThreads = 64 + kRowThreads + 32;
-constexpr int kVec = 2 * kMlp + kD;      // c0 | c1 | b2
+constexpr int kVec = 2 * kMlp + 2 * kD;  // c0 | c1 | b2 | proj bias
+constexpr int kXch = 2 * 128 * 2;        // floats: the row-owner halves exchange their LayerNorm partial sums
 constexpr int kTmemCols = 512;
 constexpr uint32_t kAcc1 = 384;          // TMEM column of the hidden-chunk accumulator
 
 struct MlpParams {
   CUtensorMap tm_hi, tm_lo;              // [M][D] bf16, box {64, 128}
+  CUtensorMap tm_att;                    // PROJ: attention output [M][D] bf16, box {64, 128}
+  CUtensorMap tm_wpa, tm_wpb;            // PROJ: proj weight [D][D], boxes {64 k, 128 rows} and {64 k, 64 rows}
+  const __nv_bfloat16 *hi_g, *lo_g;      // PROJ: the residual stream, read by the row owners themselves
+  const float* bp;                       // PROJ: proj bias
   CUtensorMap tm_w1;                     // [mlp][D], box {64 k, 64 rows}
   CUtensorMap tm_w2a, tm_w2b;            // [D][mlp], boxes {64 k, 128 rows} and {64 k, 64 rows}
   const float *c0, *c1, *b2;
@@ -67,11 +72,13 @@ struct alignas(16) Ctl {
   uint64_t x_full, x_empty[kKB], vec_full;   // x_empty[j]: the store of block j of hi' has read sX block j
   uint64_t a1_full, a1_free, h_full, h_free, acc2_full, acc2_free;
   uint64_t lo_full[kKB];                 // x_lo block j has landed (sH halves for j < 2, the idle weight ring for the rest)
+  uint64_t proj_full, x1_ready;          // PROJ: att Wp^T landed in acc2; x1 (fp32 in acc2, bf16 in sX) and the row statistics are ready
   uint64_t blk_done[kKB], fin_done;      // row owners -> store warp (output block j complete in smem); store warp -> row owners (per tile)
   uint32_t tmem_base;
 };
 
-constexpr int kSmem = kKB * kUnit + 2 * kUnit + kStages * kSlot + kVec * 4 + static_cast<int>(sizeof(Ctl)) + 1024;
+constexpr int kIdent = 4096;             // PROJ: this CTA's 32 rows of a 64 x 64 bf16 identity (B operand that adds a staged tile into acc2)
+constexpr int kSmem = kKB * kUnit + 2 * kUnit + kStages * kSlot + kIdent + (kVec + kXch) * 4 + static_cast<int>(sizeof(Ctl)) + 1024;
 static_assert(kSmem <= 227 * 1024, "shared memory budget");
 
 // arrive on a barrier of the leader CTA; release at cluster scope: the arriving CTA's smem writes (already fenced to the
@@ -108,14 +115,18 @@ __device__ __forceinline__ void ptx_prefetch_2d_e(const CUtensorMap* m, int c0, 
                    reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
 }
 
+// PROJ: the attention block's output projection runs in front of the MLP (see the file header)
+template <bool PROJ>
 __global__ void __launch_bounds__(kThreads, 1) k_enc_mlp(const __grid_constant__ MlpParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;
   uint8_t* sH = sX + kKB * kUnit;
   uint8_t* ring = sH + 2 * kUnit;
-  float* vec = reinterpret_cast<float*>(ring + kStages * kSlot);
-  Ctl* ctl = reinterpret_cast<Ctl*>(vec + kVec);
+  uint8_t* sI = ring + kStages * kSlot;
+  float* vec = reinterpret_cast<float*>(sI + kIdent);
+  float* xch = vec + kVec;
+  Ctl* ctl = reinterpret_cast<Ctl*>(xch + kXch);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = __shfl_sync(0xffffffffu, ptx::cluster_ctarank(), 0);   // 0 = leader (issues the MMAs)
@@ -140,11 +151,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_mlp(const __grid_constant__
     for (int j = 0; j < kKB; ++j) ptx::mbar_init(&ctl->lo_full[j], 1);
     for (int j = 0; j < kKB; ++j) ptx::mbar_init(&ctl->blk_done[j], kRowThreads);
     ptx::mbar_init(&ctl->fin_done, 1);
+    ptx::mbar_init(&ctl->proj_full, 1);
+    ptx::mbar_init(&ctl->x1_ready, 2 * kEpiWarps);
     ptx::fence_barrier_init();
-    ptx::mbar_arrive_expect_tx(&ctl->vec_full, kVec * 4);
+    ptx::mbar_arrive_expect_tx(&ctl->vec_full, (PROJ ? kVec : kVec - kD) * 4);
     ptx::bulk_load(vec, p.c0, kMlp * 4, &ctl->vec_full);
     ptx::bulk_load(vec + kMlp, p.c1, kMlp * 4, &ctl->vec_full);
     ptx::bulk_load(vec + 2 * kMlp, p.b2, kD * 4, &ctl->vec_full);
+    if constexpr (PROJ) ptx::bulk_load(vec + 2 * kMlp + kD, p.bp, kD * 4, &ctl->vec_full);
+  }
+  if constexpr (PROJ) {
+    // I[n][k] = (k == n), rows n = rank 32 .. + 32, K-major SWIZZLE_128B: D[:, n] += A[:, n] adds a staged bf16 tile to acc2 exactly
+    for (int i = threadIdx.x; i < kIdent / 16; i += kThreads) reinterpret_cast<uint4*>(sI)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int i = threadIdx.x, k = static_cast<int>(rank) * 32 + i;
+      *reinterpret_cast<uint16_t*>(sI + i * 128 + (((k >> 3) ^ (i & 7)) << 4) + (k & 7) * 2) = 0x3F80;   // bf16 1.0
+    }
+    ptx::fence_proxy_async();
   }
   // cluster barrier first (publishes the peer's barrier initialisation and makes sure the peer runs), then the
   // pair-collective TMEM allocation: see gemm_tc.cu / profiles/r2_hang_root_cause.md
@@ -161,9 +185,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_mlp(const __grid_constant__
     const uint32_t wfull0_c = __shfl_sync(0xffffffffu, ptx::mapa(ptx::smem_u32(&ctl->w_full[0]), 0), 0);
     int stage = 0;
     uint32_t phase = 0, it_par = 0, n_it = 0;
-    auto slot_begin = [&]() -> uint8_t* {
+    auto slot_begin = [&](uint32_t bytes = kSlot) -> uint8_t* {
       ptx::mbar_wait(&ctl->w_empty[stage], phase ^ 1); __syncwarp();
-      if (rank == 0) ptx::mbar_arrive_expect_tx_e(&ctl->w_full[stage], 2u * kSlot);   // the leader's barrier counts both CTAs' bytes
+      if (rank == 0) ptx::mbar_arrive_expect_tx_e(&ctl->w_full[stage], 2u * bytes);   // the leader's barrier counts both CTAs' bytes
       return ring + stage * kSlot;
     };
     auto slot_end = [&]() { if (++stage == kStages) { stage = 0; phase ^= 1; } };
@@ -191,11 +215,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_mlp(const __grid_constant__
       if (rank == 0) ptx::mbar_arrive_expect_tx_e(&ctl->x_full, 2u * kKB * kUnit);
       for (int kb = 0; kb < kKB; ++kb) {
         ptx::mbar_wait(&ctl->x_empty[kb], it_par ^ 1); __syncwarp();
-        ptx::tma_load_2d_pair_e(sX + kb * kUnit, &p.tm_hi, xfull_c, kb * 64, m0);
+        ptx::tma_load_2d_pair_e(sX + kb * kUnit, PROJ ? &p.tm_att : &p.tm_hi, xfull_c, kb * 64, m0);
       }
       if (n_it > 0) { ptx::mbar_wait(&ctl->fin_done, (n_it - 1) & 1); __syncwarp(); }
       ++n_it;
       const bool more = t + n_pairs < p.n_tiles;
+      if constexpr (PROJ) {   // the output projection's weights: 6 k-blocks, the slot layout of fc2
+        for (int kb = 0; kb < kKB; ++kb) {
+          uint8_t* dst = slot_begin();
+          const uint32_t bar = wfull0_c + stage * 8;
+          ptx::tma_load_2d_pair_e(dst, &p.tm_wpa, bar, kb * 64, static_cast<int>(rank) * 128);
+          ptx::tma_load_2d_pair_e(dst + kUnit, &p.tm_wpb, bar, kb * 64, 256 + static_cast<int>(rank) * 64);
+          slot_end();
+        }
+        // the residual rows x = hi + lo, block by block: the MMA issuer adds them into acc2 through the identity operand
+        for (int j2 = 0; j2 < 2 * kKB; ++j2) {
+          uint8_t* dst = slot_begin(kUnit);
+          const uint32_t bar = wfull0_c + stage * 8;
+          ptx::tma_load_2d_pair_e(dst, j2 < kKB ? &p.tm_hi : &p.tm_lo, bar, (j2 % kKB) * 64, m0);
+          slot_end();
+        }
+      }
       // the MMA issuer's order: W1(0), then per chunk W1(c) before W2(c - 1), W2(last)
       load_w1(0, 0); load_w1(0, 1);
       for (int c = 1; c < kNC; ++c) {
@@ -203,11 +243,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_mlp(const __grid_constant__
         load_w2(c - 1, 0); load_w2(c - 1, 1);
         // this tile's x_lo blocks and the next tile's x_hi rows towards L2, one box per chunk (all at once they queue in
         // front of the weight loads): both are needed at the tile boundary, where their latency is exposed
-        if (c <= kKB) ptx_prefetch_2d_e(&p.tm_lo, (c - 1) * 64, m0);
-        else if (more) ptx_prefetch_2d_e(&p.tm_hi, (c - 1 - kKB) * 64, m0 + n_pairs * 256);
+        if constexpr (PROJ) {   // the next tile's attention rows and residual rows
+          if (more) {
+            if (c <= kKB) ptx_prefetch_2d_e(&p.tm_att, (c - 1) * 64, m0 + n_pairs * 256);
+            else ptx_prefetch_2d_e(&p.tm_hi, (c - 1 - kKB) * 64, m0 + n_pairs * 256);
+          }
+        } else {
+          if (c <= kKB) ptx_prefetch_2d_e(&p.tm_lo, (c - 1) * 64, m0);
+          else if (more) ptx_prefetch_2d_e(&p.tm_hi, (c - 1 - kKB) * 64, m0 + n_pairs * 256);
+        }
       }
       load_w2(kNC - 1, 0); load_w2(kNC - 1, 1);
       if (more) ptx_prefetch_2d_e(&p.tm_hi, (kKB - 1) * 64, m0 + n_pairs * 256);
+      if constexpr (PROJ) {
+        if (more)
+          for (int j = 0; j < kKB; ++j) ptx_prefetch_2d_e(&p.tm_lo, j * 64, m0 + n_pairs * 256);
+        continue;   // no x_lo staging: the residual was folded into acc2 at the start of the tile
+      }
       // every MMA of the tile has completed: sH and the whole weight ring are idle, together they take the tile's six
       // x_lo blocks at once (one HBM round trip instead of one per block)
       ptx::mbar_wait(&ctl->acc2_full, it_par); __syncwarp();
@@ -257,14 +309,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_mlp(const __grid_constant__
       auto mma2 = [&](int c) {   // acc2 (+)= GELU(h_c) W2_c^T
         TT_TIMED(w_h, wait_cluster(&ctl->h_full, n2 & 1)); __syncwarp();
         ++n2;
-        if (c == 0) { TT_TIMED(w_acc2, ptx::mbar_wait(&ctl->acc2_free, it_par ^ 1)); __syncwarp(); }   // the previous tile's rows have been read out
+        if (!PROJ && c == 0) { TT_TIMED(w_acc2, ptx::mbar_wait(&ctl->acc2_free, it_par ^ 1)); __syncwarp(); }   // the previous tile's rows have been read out
         ptx::tc_fence_after();
         for (int kb2 = 0; kb2 < 2; ++kb2) {
           const uint32_t b_addr = slot_wait();
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t da = ptx::make_smem_desc(h_addr + kb2 * kUnit + k * 32, 128);
-            const uint32_t acc = (c | kb2 | k) != 0 ? 1u : 0u;
+            const uint32_t acc = (PROJ || (c | kb2 | k) != 0) ? 1u : 0u;   // PROJ: onto x1, which the row owners wrote into acc2
             ptx::mma_bf16_pair_e(acc2, da, ptx::make_smem_desc(b_addr + k * 32, 128), idesc2a, acc);
             ptx::mma_bf16_pair_e(acc2 + 256, da, ptx::make_smem_desc(b_addr + kUnit + k * 32, 128), idesc2b, acc);
           }
@@ -275,6 +327,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_mlp(const __grid_constant__
       for (int t = pair; t < p.n_tiles; t += n_pairs, it_par ^= 1) {
         TT_TIMED(w_x, ptx::mbar_wait(&ctl->x_full, it_par)); __syncwarp();
         ptx::tc_fence_after();
+        if constexpr (PROJ) {
+          // acc2 = att Wp^T, then the row owners turn it into x1 = x + acc2 + bias (fp32 back into acc2, bf16 into sX)
+          TT_TIMED(w_acc2, ptx::mbar_wait(&ctl->acc2_free, it_par ^ 1)); __syncwarp();
+          ptx::tc_fence_after();
+          for (int kb = 0; kb < kKB; ++kb) {
+            const uint32_t b_addr = slot_wait();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = ptx::make_smem_desc(x_addr + kb * kUnit + k * 32, 128);
+              const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+              ptx::mma_bf16_pair_e(acc2, da, ptx::make_smem_desc(b_addr + k * 32, 128), idesc2a, acc);
+              ptx::mma_bf16_pair_e(acc2 + 256, da, ptx::make_smem_desc(b_addr + kUnit + k * 32, 128), idesc2b, acc);
+            }
+            slot_done();
+          }
+          const uint32_t idesc3 = ptx::make_idesc_bf16(256, 64), i_addr = ptx::smem_u32(sI);
+          for (int j2 = 0; j2 < 2 * kKB; ++j2) {   // acc2[:, 64 j .. + 64) += hi / lo block j
+            const uint32_t a_addr = slot_wait();
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::mma_bf16_pair_e(acc2 + (j2 % kKB) * 64, ptx::make_smem_desc(a_addr + k * 32, 128), ptx::make_smem_desc(i_addr + k * 32, 128), idesc3, 1u);
+            slot_done();
+          }
+          ptx::mma_commit_pair_e(&ctl->proj_full, 3);
+          TT_TIMED(w_x, wait_cluster(&ctl->x1_ready, it_par)); __syncwarp();
+          ptx::tc_fence_after();
+        }
         mma1();
         for (int c = 1; c < kNC; ++c) { mma1(); mma2(c - 1); }
         mma2(kNC - 1);
@@ -324,9 +403,57 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_mlp(const __grid_constant__
       const long long m0 = static_cast<long long>(t * 2 + static_cast<int>(rank)) * 128;
       const long long row = m0 + r;
       const bool row_ok = row < p.M;
-      // LayerNorm of this row from the producer's two partial sums
       float s1 = 0.f, s2 = 0.f;
-      if (row_ok) {
+      if constexpr (PROJ) {
+        // ---- acc2 = x + att Wp^T (the MMA issuer added the residual rows through the identity operand); x1 = acc2 + bias:
+        //      bf16(x1) into sX (fc1's A operand) and the row's LayerNorm sums.  acc2 itself stays as it is: fc2 accumulates
+        //      onto it and the final phase adds both biases.
+        const uint32_t x1_ready_c = ptx::mapa(ptx::smem_u32(&ctl->x1_ready), 0);
+        ptx::mbar_wait(&ctl->proj_full, it_par);
+        ptx::tc_fence_after();
+        uint64_t q1 = 0ull, q2 = 0ull;
+        uint32_t rb0[2][32];
+        ptx::tmem_ld<32>(tl + half * 32, rb0[0]);
+#pragma unroll
+        for (int j = 0; j < kKB; ++j) {
+          uint32_t (&raw)[32] = rb0[j & 1];
+          ptx::tmem_ld_wait(raw);
+          if (j + 1 < kKB) ptx::tmem_ld<32>(tl + (j + 1) * 64 + half * 32, rb0[(j + 1) & 1]);
+          const uint32_t xrow = ptx::smem_u32(sX) + j * kUnit + r * 128;
+          const uint32_t bp_s = vec_s + (2 * kMlp + kD + j * 64 + half * 32) * 4;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 b0 = ptx::lds128(bp_s + g * 32), b1 = ptx::lds128(bp_s + g * 32 + 16);
+            const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint32_t ho[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint64_t v = add2(pk2u(raw[8 * g + 2 * e], raw[8 * g + 2 * e + 1]), pk2u(bw[2 * e], bw[2 * e + 1]));
+              q1 = add2(q1, v);
+              q2 = fma2(v, v, q2);
+              float x0, x1;
+              upk2(v, x0, x1);
+              ho[e] = pack_bf16(x0, x1);
+            }
+            ptx::sts128(xrow + ((static_cast<uint32_t>(half * 4 + g) ^ sw) << 4), make_uint4(ho[0], ho[1], ho[2], ho[3]));
+          }
+        }
+        {
+          float a0, a1, b0, b1;
+          upk2(q1, a0, a1);
+          upk2(q2, b0, b1);
+          s1 = a0 + a1; s2 = b0 + b1;
+          xch[(half * 128 + r) * 2] = s1;
+          xch[(half * 128 + r) * 2 + 1] = s2;
+          ptx::named_bar_sync<2, kRowThreads>();
+          s1 += xch[((half ^ 1) * 128 + r) * 2];
+          s2 += xch[((half ^ 1) * 128 + r) * 2 + 1];
+        }
+        ptx::fence_proxy_async();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(x1_ready_c);
+      } else if (row_ok) {   // LayerNorm of this row from the producer's two partial sums
         const float2* st = reinterpret_cast<const float2*>(p.stats) + row * 2;
         const float2 a = __ldg(st), b = __ldg(st + 1);
         s1 = a.x + b.x; s2 = a.y + b.y;
@@ -388,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_mlp(const __grid_constant__
 #pragma unroll
       for (int j = 0; j < kKB; ++j) {
         uint32_t (&raw)[32] = rbuf[j & 1];
-        ptx::mbar_wait(&ctl->lo_full[j], it_par);
+        if constexpr (!PROJ) ptx::mbar_wait(&ctl->lo_full[j], it_par);
         ptx::tmem_ld_wait(raw);
         if (j + 1 < kKB) ptx::tmem_ld<32>(tl + (j + 1) * 64 + half * 32, rbuf[(j + 1) & 1]);   // in flight during this block's math
         const uint32_t xrow = ptx::smem_u32(sX) + j * kUnit + r * 128;
@@ -397,10 +524,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_enc_mlp(const __grid_constant__
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const uint32_t off = ((static_cast<uint32_t>(half * 4 + g) ^ sw) << 4);
-          const uint4 hv = ptx::lds128(xrow + off), lv = ptx::lds128(lrow + off);
+          const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+          const uint4 hv = PROJ ? zero4 : ptx::lds128(xrow + off), lv = PROJ ? zero4 : ptx::lds128(lrow + off);   // PROJ: acc2 already holds x1
           const uint4 b0 = ptx::lds128(b2_s + g * 32), b1 = ptx::lds128(b2_s + g * 32 + 16);
           const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
-          const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          if constexpr (PROJ) {   // + the projection's bias: acc2 holds x + att Wp^T + the MLP update
+            const uint4 p0 = ptx::lds128(b2_s + kD * 4 + g * 32), p1 = ptx::lds128(b2_s + kD * 4 + g * 32 + 16);
+            const uint32_t pw[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bw[i] = __float_as_uint(__uint_as_float(bw[i]) + __uint_as_float(pw[i]));
+          }
           uint32_t ho[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {   // two columns per 32-bit word: low half = even column
@@ -455,9 +589,9 @@ bool make_map(CUtensorMap* m, const void* base, long long rows, int cols, int bo
 bool enc_mlp_supported(int D, int mlp) { return D == kD && mlp == kMlp; }
 
 cudaError_t enc_mlp_forward(const EncMlpWeights& w, __nv_bfloat16* hi, __nv_bfloat16* lo, float* stats, int parts_in,
-                            long long M, int D, int mlp, float eps, cudaStream_t s) {
+                            long long M, int D, int mlp, float eps, cudaStream_t s, const EncProj* proj) {
   if (M <= 0) return cudaSuccess;
-  if (!enc_mlp_supported(D, mlp) || parts_in != 2) {
+  if (!enc_mlp_supported(D, mlp) || (proj == nullptr && parts_in != 2)) {
     set_error("enc_mlp: built for PARSeq-base (embed 384, MLP 1536) with two LayerNorm partials per row");
     return cudaErrorInvalidValue;
   }
@@ -470,6 +604,13 @@ cudaError_t enc_mlp_forward(const EncMlpWeights& w, __nv_bfloat16* hi, __nv_bflo
       !make_map(&p.tm_w2a, w.w2, D, mlp, 128) || !make_map(&p.tm_w2b, w.w2, D, mlp, 64))
     return cudaErrorInvalidValue;
   p.c0 = w.c0; p.c1 = w.c1; p.b2 = w.b2;
+  if (proj) {
+    if (reinterpret_cast<uintptr_t>(proj->bp) & 15) { set_error("enc_mlp: proj bias must be 16-byte aligned"); return cudaErrorInvalidValue; }
+    if (!make_map(&p.tm_att, proj->att, M, D, 128) || !make_map(&p.tm_wpa, proj->wp, D, D, 128) || !make_map(&p.tm_wpb, proj->wp, D, D, 64))
+      return cudaErrorInvalidValue;
+    p.bp = proj->bp;
+    p.hi_g = hi; p.lo_g = lo;
+  }
   p.stats = stats;
   p.M = M;
   p.n_tiles = static_cast<int>((M + 255) / 256);
@@ -479,7 +620,8 @@ cudaError_t enc_mlp_forward(const EncMlpWeights& w, __nv_bfloat16* hi, __nv_bflo
   if (dbg_on && !dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long));
   if (dbg_on) cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), s);
   p.dbg = dbg_on ? dbg_buf : nullptr;
-  TT_CUDA_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(k_enc_mlp), kSmem));
+  const void* fn = proj ? reinterpret_cast<const void*>(k_enc_mlp<true>) : reinterpret_cast<const void*>(k_enc_mlp<false>);
+  TT_CUDA_TRY(ensure_dynamic_smem(fn, kSmem));
   // co-resident CTA pairs (one per TPC: 74 on a full B200)
   static int max_pairs = 0;
   if (max_pairs == 0) {
@@ -490,7 +632,7 @@ cudaError_t enc_mlp_forward(const EncMlpWeights& w, __nv_bfloat16* hi, __nv_bflo
     qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
     qc.attrs = qa; qc.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, reinterpret_cast<const void*>(k_enc_mlp), &qc) != cudaSuccess || n <= 0) n = 64;
+    if (cudaOccupancyMaxActiveClusters(&n, fn, &qc) != cudaSuccess || n <= 0) n = 64;
     max_pairs = n;
   }
   const int pairs = std::min(p.n_tiles, max_pairs);
@@ -504,7 +646,14 @@ cudaError_t enc_mlp_forward(const EncMlpWeights& w, __nv_bfloat16* hi, __nv_bflo
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  TT_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_enc_mlp, p));
+  char tag[96];
+  if (prof_enabled()) {
+    std::snprintf(tag, sizeof(tag), "mlp M%lld D%d H%d grid%d pair fused %sfc1+gelu+fc2", M, D, mlp, 2 * pairs, proj ? "proj+" : "");
+    prof_record(s, true, 0, 0);
+  }
+  if (proj) TT_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_enc_mlp<true>, p));
+  else TT_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_enc_mlp<false>, p));
+  prof_record(s, false, 4.0 * static_cast<double>(M) * D * mlp + (proj ? 2.0 * static_cast<double>(M) * D * D : 0.0), 0, tag);   // fc1 + fc2 (+ proj)
   TT_LAUNCH_CHECK();
   if (dbg_on) {
     unsigned long long h[16];

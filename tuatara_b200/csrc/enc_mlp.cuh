@@ -16,11 +16,21 @@ struct EncMlpWeights {
   const float* b2 = nullptr;           // [D]
 };
 
+// The attention block's output projection in front of the MLP: x1 = x + att Wp^T + bp is formed inside the kernel (fp32 in
+// TMEM, where fc2 accumulates onto it; bf16 in smem as fc1's operand; its LayerNorm sums in registers) instead of
+// travelling to HBM and back between two kernels.
+struct EncProj {
+  const __nv_bfloat16* att = nullptr;  // [M][D] attention output
+  const __nv_bfloat16* wp = nullptr;   // [D][D]
+  const float* bp = nullptr;           // [D]
+};
+
 bool enc_mlp_supported(int D, int mlp);
 
 // x = hi + lo (split bf16 residual stream, [M][D] each, updated in place); stats: per row `parts_in` partial
 // (sum x, sum x^2) float2 on entry, 2 partials on return (columns [0, D/2) and [D/2, D)).
+// proj != null: x = x + att Wp^T + bp first (stats are not read then, only written).
 cudaError_t enc_mlp_forward(const EncMlpWeights& w, __nv_bfloat16* hi, __nv_bfloat16* lo, float* stats, int parts_in,
-                            long long M, int D, int mlp, float eps, cudaStream_t s);
+                            long long M, int D, int mlp, float eps, cudaStream_t s, const EncProj* proj = nullptr);
 
 }  // namespace tt

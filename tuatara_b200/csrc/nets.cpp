@@ -293,6 +293,8 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
   // on the SM.  TT_ENC_MLPFUSE=0 keeps the two GEMM launches (A/B runs, parity test); PARSeq-tiny always takes them.
   const char* mf_env = std::getenv("TT_ENC_MLPFUSE");   // read per call: the parity test flips it in-process
   const bool mlp_fuse = lnf && !(mf_env && std::atoi(mf_env) == 0) && enc_mlp_supported(D, pd.mlp);
+  const char* pf_env = std::getenv("TT_ENC_PROJFUSE");   // 0: the attention output projection stays a GEMM launch (A/B runs)
+  const bool proj_fuse = !(pf_env && std::atoi(pf_env) == 0);
   ARENA_GET(x, float, Mc * D);       // fp32 residual stream (unfused) / the lo half of the split stream (fused; first half of the buffer)
   ARENA_GET(h, bf, Mc * D);          // LayerNorm output (unfused) / the hi half of the split stream = bf16(x) (fused)
   bf* const x_lo = reinterpret_cast<bf*>(x);
@@ -346,6 +348,17 @@ cudaError_t DeviceCtx::parseq_forward(const __nv_bfloat16* patches, int n, const
       if (!lnf) RUN(layernorm(x, Mi, D, wf.f32(p + "ln1.g"), wf.f32(p + "ln1.b"), 1e-6f, h, nullptr, 0, s));
       RUN(ln_gemm(p + "qkv", Mi, 3 * D, ACT_NONE, qkv));
       RUN(attention_enc(qkv, att, nc, D, pd.enc_heads, s));
+      if (mlp_fuse && proj_fuse) {
+        // proj + residual + fc1 -> GELU -> fc2 + residual in one kernel: x1 never leaves the SM either (enc_mlp.cu)
+        EncMlpWeights mw;
+        mw.w1 = wf.bf(p + "fc1.wf"); mw.c0 = wf.f32(p + "fc1.c0"); mw.c1 = wf.f32(p + "fc1.c1");
+        mw.w2 = wf.bf(p + "fc2.w"); mw.b2 = wf.f32(p + "fc2.b");
+        EncProj pj;
+        pj.att = att; pj.wp = wf.bf(p + "proj.w"); pj.bp = wf.f32(p + "proj.b");
+        RUN(enc_mlp_forward(mw, h, x_lo, lnstats, 2, Mi, D, pd.mlp, 1e-6f, s, &pj));
+        ln_parts = 2;
+        continue;
+      }
       RUN(res_gemm(att, D, Mi, D, wf.bf(p + "proj.w"), wf.f32(p + "proj.b"), nullptr, 0));
       if (mlp_fuse && ln_parts == 2) {
         // fc1 -> GELU -> fc2 -> residual in one kernel: the hidden activations stay on the SM (enc_mlp.cu)
