@@ -17,6 +17,8 @@ for k in k_dec_dense k_dec_cross_attn; do
   TT_DEC_EARLY_EXIT=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 60 -c 2 -f \
     -o gpurun_out/prof_${k}_$TAG python tools/dec_bench.py 9600 > gpurun_out/ncu_${k}_$TAG.log 2>&1; echo "$k rc=$?"
 done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_enc_mlp -s 14 -c 1 -f \
+    -o gpurun_out/prof_k_enc_mlp_$TAG python tools/dec_bench.py 9600 > gpurun_out/ncu_k_enc_mlp_$TAG.log 2>&1; echo "k_enc_mlp rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_attn_enc -s 14 -c 1 -f \
     -o gpurun_out/prof_k_attn_enc_$TAG python tools/dec_bench.py 9600 > gpurun_out/ncu_k_attn_enc_$TAG.log 2>&1; echo "k_attn_enc rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_conv1_1 -s 2 -c 1 -f \

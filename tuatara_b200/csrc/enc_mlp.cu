@@ -1,22 +1,31 @@
-// Fused MLP block of the PARSeq encoder:  x += fc2(GELU(fc1(LN2(x)))) in ONE tcgen05 kernel (see enc_mlp.cuh).
+// Second half of a PARSeq encoder block in ONE tcgen05 kernel (see enc_mlp.cuh):
+//     x1 = x + att Wp^T + bp            (the attention output projection; template PROJ)
+//     x' = x1 + fc2(GELU(fc1(LN2(x1))))
 //
-// Why: as two GEMM launches (gemm_tc.cu) the [rows][1536] bf16 hidden tensor makes a 1.9 GB HBM round trip per layer and
-// 2400 crops, and both GEMMs are paced by the shared-memory port: the hidden tile is written to
-// staging buffers, read back by a TMA store, and brought in again by TMA as fc2's A operand.  Here a CTA pair owns 256
-// rows for the whole block: GELU(fc1 chunk) goes from registers straight into the smem tile that fc2's MMA reads.
+// Why: as GEMM launches (gemm_tc.cu: proj, fc1, fc2) x1 makes an HBM round trip between proj and the MLP and the
+// [rows][1536] bf16 hidden tensor a 1.9 GB one per layer and 2400 crops, and the GEMMs are paced by the shared-memory port
+// (DESIGN.md section 6): the hidden tile is written to staging buffers, read back by a TMA store, and brought in again by
+// TMA as fc2's A operand.  Here a CTA pair owns 256 rows for the whole chain: GELU(fc1 chunk) goes from registers straight
+// into the smem tile that fc2's MMA reads, x1 lives in TMEM.  At the 1000 W cap the removed traffic also shows as SM clock.
 //
 // A CTA pair (cta_group::2, one TPC) per 256-row tile, each CTA 128 rows = 128 TMEM lanes; per CTA
-//   warp 0      TMA producer : the tile's x_hi rows -> sX (A operand of fc1, 6 k-blocks, resident for the tile); the
-//                              weights of the 12 hidden chunks through a ring of 24 KB slots (this CTA's half of the
-//                              rows: 64 of a chunk's 128 fc1 rows, 192 of fc2's 384); at the end the tile's x_lo blocks
-//   warp 1      MMA issuer   : (leader CTA only)  acc1[128 cols] = x W1_c^T, acc2[384 cols] += GELU(h_c) W2_c^T,
+//   warp 0      TMA producer : the tile's A rows -> sX (PROJ: att, else x_hi; 6 k-blocks, resident for the tile); through a
+//                              ring of 24 KB slots this CTA's half of every weight tile (PROJ: Wp, then the residual rows
+//                              hi / lo block by block; then per hidden chunk 64 of its 128 fc1 rows and 192 of fc2's 384);
+//                              L2 prefetches of the next tile's rows, one box per chunk
+//   warp 1      MMA issuer   : (leader CTA only)  PROJ: acc2 = att Wp^T, then acc2 += hi + lo: each staged residual block
+//                              is the A operand of an MMA whose B operand is a 64 x 64 identity (exact in fp32, no thread
+//                              touches the residual).  acc1[128 cols] = x1 W1_c^T, acc2[384 cols] += GELU(h_c) W2_c^T,
 //                              software pipelined: fc1 of chunk c+1 is issued before fc2 of chunk c, so the tensor pipe
 //                              works while the row owners evaluate GELU(c)
-//   warps 2..9  row owners   : thread = row; two warps per TMEM lane quadrant, 64 hidden columns each.  LayerNorm is applied
-//                              algebraically (rstd * acc - rstd * mean * c1 + c0, as gemm_tc.cu's consumer epilogue),
-//                              GELU, bf16 -> sH (K-major SWIZZLE_128B).  Final phase: x' = acc2 + b2 + hi + lo in fp32,
-//                              hi' = bf16(x'), lo' = bf16(x' - hi') written over the staged tiles and TMA-stored, the
-//                              row's (sum, sum of squares) emitted for the next layer's LayerNorm.
+//   warps 2..9  row owners   : thread = row; two warps per TMEM lane quadrant.  PROJ: bf16(acc2 + bp) -> sX (fc1's A
+//                              operand, over the att tile) and the row's LayerNorm sums (the two halves meet in smem).
+//                              Per chunk: LayerNorm applied algebraically (rstd * acc - rstd * mean * c1 + c0, as
+//                              gemm_tc.cu's consumer epilogue), GELU, bf16 -> sH (K-major SWIZZLE_128B).  Final phase:
+//                              x' = acc2 + b2 (+ bp) [+ hi + lo without PROJ: x_lo staged in sH and the idle ring] in fp32,
+//                              hi' = bf16(x'), lo' = bf16(x' - hi') written over the staged tiles, the row's
+//                              (sum, sum of squares) emitted for the next layer's LayerNorm
+//   warp 10     store warp   : hands each finished 64-column block of hi' / lo' to TMA stores and releases its smem
 // TMEM: columns [0, 384) = acc2 (the block's output rows), [384, 512) = acc1 (one hidden chunk).
 // Every wait is bounded (ptx::mbar_wait traps after 4 s).
 #include "enc_mlp.cuh"
