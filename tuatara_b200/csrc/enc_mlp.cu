@@ -631,9 +631,8 @@ cudaError_t enc_mlp_forward(const EncMlpWeights& w, __nv_bfloat16* hi, __nv_bflo
   p.dbg = dbg_on ? dbg_buf : nullptr;
   const void* fn = proj ? reinterpret_cast<const void*>(k_enc_mlp<true>) : reinterpret_cast<const void*>(k_enc_mlp<false>);
   TT_CUDA_TRY(ensure_dynamic_smem(fn, kSmem));
-  // co-resident CTA pairs (one per TPC: 74 on a full B200)
-  static int max_pairs = 0;
-  if (max_pairs == 0) {
+  // co-resident CTA pairs (one per TPC: 74 on a full B200; all GPUs of a box are the same part), queried once
+  static const int max_pairs = [&]() {
     cudaLaunchConfig_t qc{};
     qc.gridDim = dim3(2); qc.blockDim = dim3(kThreads); qc.dynamicSmemBytes = kSmem;
     cudaLaunchAttribute qa[1];
@@ -641,9 +640,9 @@ cudaError_t enc_mlp_forward(const EncMlpWeights& w, __nv_bfloat16* hi, __nv_bflo
     qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
     qc.attrs = qa; qc.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, fn, &qc) != cudaSuccess || n <= 0) n = 64;
-    max_pairs = n;
-  }
+    if (cudaOccupancyMaxActiveClusters(&n, fn, &qc) != cudaSuccess || n <= 0) n = 64;   // fn: its dynamic smem limit is set
+    return n;
+  }();
   const int pairs = std::min(p.n_tiles, max_pairs);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
