@@ -453,6 +453,8 @@ def run_native(args, rank, local_rank, world):
                    "weights": "seeded random init (CRAFT VGG16-BN, PARSeq-base)", "parallelism": f"dp{world} (pages)",
                    "slots_per_gpu": env_int("TT_SLOTS", 3), "work_queue": "detection units of <= 8 pages pulled by the slots; crops of all sizes share PARSeq batches",
                    "kernel_paths": "conservative (retry after a failed first attempt)" if os.environ.get("TT_BENCH_RETRY") else "default",
+                   "encoder": "per block: qkv GEMM (LayerNorm in its epilogue), attention, then proj + residual + MLP + residual as one kernel "
+                              "(k_enc_mlp); bf16 operands, fp32 accumulation, fp32-equivalent split residual stream",
                    "decoder": "26-step AR schedule with per-crop exit at EOS (upstream PARSeq's early exit, which the reference applies per "
                               "4-crop forward; outputs identical to the full schedule: test_parseq_early_exit_is_output_preserving) + 1 refinement; "
                               "the CPU baseline / reference arm run the oracle with the same exit per 4-crop chunk",
