@@ -383,6 +383,13 @@ def run_native(args, rank, local_rank, world):
     prof_steps = min(args.steps, 2)
     r_prof = timed(step_dev, prof_steps, profile=True)
     lib.tt_engine_set_slots(eng._h, env_int("TT_SLOTS", 3))
+    # for the record: the same step with the full 26-step AR schedule (no per-crop exit at EOS; same outputs)
+    r_full = None
+    if os.environ.get("TT_DEC_EARLY_EXIT", "1") != "0" and not args.no_configs:
+        os.environ["TT_DEC_EARLY_EXIT"] = "0"              # read per call by the engine
+        step_dev()
+        r_full = timed(step_dev, 1)
+        del os.environ["TT_DEC_EARLY_EXIT"]
 
     peaks = measured_peaks()
     # BASELINE.json's second metric: PARSeq crops/s on a batch of 1024 synthetic 32x128 crops (configs[2]),
@@ -473,6 +480,9 @@ def run_native(args, rank, local_rank, world):
                      "algorithmic_gflop_per_step": n * (CRAFT_GFLOP_PER_PAGE + WORDS * PARSEQ_ENC_GFLOP_PER_CROP)
                                                    + stages.get("parseq_decoder", {}).get("flops", 0.0) / 1e9}),
         "roofline_other": other,
+        "full_ar_schedule": None if r_full is None else {
+            "value": job_throughput(n, world, 1, r_full["ms"]), "unit": "pages/s", "steps": 1,
+            "note": "same step with TT_DEC_EARLY_EXIT=0: every crop runs all 26 AR steps (outputs identical)"},
         "stages": stage_lines,
         "parseq": {"crops_per_s": parseq_cps, "batch": 1024, "frac_tensor": parseq_cps * PARSEQ_ENC_GFLOP_PER_CROP / 1e3 / peaks["tf_sustained"],
                    "note": "configs[2]: 1024 synthetic 32x128 crops, PARSeq-base, AR pass (<= 26 steps, per-crop exit at EOS) + refinement, "
